@@ -1,0 +1,164 @@
+/*
+ * alz_b200.h -- C ABI of the B200-native AudioLazy filter hot path.
+ *
+ * This is the drop-in boundary for ONE path of danilobellini/audiolazy: the
+ * sample-by-sample linear filter evaluator and its composites.  The reference
+ * has no FFI; its operator contract is "a filter is any callable that receives
+ * an iterable and returns a Stream" (reference audiolazy/lazy_filters.py:975-978,
+ * :1033-1036).  The entry points below are what a ctypes binding of that path
+ * binds (see INTEGRATION.md for the stub a reference maintainer would add):
+ *
+ *   alz_plan_create      <- the per-call source generation + exec of
+ *                           LinearFilter.__call__ (lazy_filters.py:197-260):
+ *                           "compile" a filter (or a bank of cascades) once.
+ *   alz_state_init       <- memory=/zero= seeding (lazy_filters.py:181-195,
+ *                           :243-250).
+ *   alz_apply_f32        <- the generated `for d0 in seq:` loop
+ *                           (lazy_filters.py:251-257), CascadeFilter.__call__
+ *                           (:988-990) and the bank fan-out loop
+ *                           (examples/gammatone_plots.py:63-71), on DEVICE buffers.
+ *   alz_apply_f32_host   <- the same through HOST buffers (what a Stream block
+ *                           pump or any host caller uses); copies are inside.
+ *   alz_sum_channels_f32 <- ParallelFilter.__call__'s left-associated
+ *                           elementwise sum (lazy_filters.py:1048-1054).
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross the ABI; every
+ * function returns 0 on success or a negative alz_status; alz_last_error() gives a
+ * thread-local message for the last failure.  The caller owns every buffer.  Calls
+ * are asynchronous with respect to the given CUDA stream unless stated otherwise.
+ * A plan is immutable after creation and may be used concurrently from several
+ * host threads / CUDA streams as long as each call uses its own state buffer.
+ *
+ * There is NO CPU implementation behind this ABI.  Every compute entry point
+ * fails (ALZ_ERR_CUDA) when no CUDA device is usable.
+ */
+#ifndef ALZ_B200_H
+#define ALZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALZ_ABI_VERSION 1
+
+typedef enum alz_status {
+  ALZ_OK = 0,
+  ALZ_ERR_INVALID = -1,    /* bad argument (null pointer, negative size, ...)          */
+  ALZ_ERR_NONCAUSAL = -2,  /* reserved: host layer raises ValueError("Non-causal filter") */
+  ALZ_ERR_ZERO_GAIN = -3,  /* a0 == 0: reference raises ZeroDivisionError (lazy_filters.py:177-178) */
+  ALZ_ERR_CUDA = -4,       /* CUDA runtime failure or no device                        */
+  ALZ_ERR_NOMEM = -5,
+  ALZ_ERR_UNSUPPORTED = -6
+} alz_status;
+
+/* Which kernel family a plan dispatches to. */
+typedef enum alz_kind {
+  ALZ_KIND_BIQUAD = 1,   /* every section has <=3 numerator and <=3 denominator taps  */
+  ALZ_KIND_GENERIC = 2   /* arbitrary (sparse) taps, ring-buffer history              */
+} alz_kind;
+
+typedef struct alz_plan alz_plan;
+
+typedef struct alz_plan_info {
+  int32_t abi_version;
+  int32_t kind;              /* alz_kind                                              */
+  int32_t n_channels;        /* C: independent cascades fed by the same input stream  */
+  int32_t n_sections;        /* K: sections per cascade after padding                 */
+  int32_t num_taps;          /* NB template value (biquad kind) or max nb (generic)   */
+  int32_t monic;             /* 1 if b0 was factored out of every section             */
+  int32_t state_doubles;     /* doubles of state per (stream, channel)                */
+  int32_t fp64_ops;          /* FP64 instructions per channel-sample in the hot loop  */
+  int32_t device;            /* CUDA device ordinal the plan lives on                 */
+  int32_t reserved[7];
+} alz_plan_info;
+
+/* Thread-local description of the last error returned on this thread. */
+const char* alz_last_error(void);
+
+/* ABI version of the loaded library (== ALZ_ABI_VERSION it was built with). */
+int32_t alz_abi_version(void);
+
+/* Number of usable CUDA devices (0 if none; never fails). */
+int32_t alz_device_count(void);
+
+/*
+ * Build a plan for a bank of `n_channels` cascades of up to `max_sections`
+ * direct-form-I sections on the CURRENT CUDA device.
+ *
+ *   section_desc[(c*max_sections + k)*3 + 0] = nb  (numerator taps, 0 => section absent)
+ *   section_desc[(c*max_sections + k)*3 + 1] = na  (denominator taps incl. a0, >= 1)
+ *   section_desc[(c*max_sections + k)*3 + 2] = offset into coef[]
+ *   coef[offset .. offset+nb)        = b[0..nb)   (ascending delay, zeros allowed)
+ *   coef[offset+nb .. offset+nb+na)  = a[0..na)   (a[0] is the gain divisor)
+ *
+ * Each section computes, per sample (reference lazy_filters.py:197-257):
+ *   y[n] = (sum_k b[k] x[n-k] - sum_{k>=1} a[k] y[n-k]) / a[0]
+ * Absent sections (nb == 0) must be trailing; a channel with no sections is the
+ * identity (empty CascadeFilter, reference tests/test_filters.py:557-561).
+ */
+int32_t alz_plan_create(const double* coef, const int32_t* section_desc,
+                        int32_t n_channels, int32_t max_sections, alz_plan** out);
+
+void alz_plan_destroy(alz_plan* plan);
+
+int32_t alz_plan_info_get(const alz_plan* plan, alz_plan_info* out);
+
+/* Doubles of device state needed for `n_streams` input streams (>= 0), or <0 on error. */
+int64_t alz_plan_state_doubles(const alz_plan* plan, int64_t n_streams);
+
+/*
+ * Initialise a device state buffer.  xinit / yinit are HOST arrays (or NULL for
+ * zeros) shaped [n_channels][n_sections][xd] and [n_channels][n_sections][yd]
+ * where xd / yd are returned by alz_plan_history(): entry j is the value the
+ * reference would hold in d{j+1} (input pre-history, `zero`) and m{j+1}
+ * (`memory`), lazy_filters.py:243-250.  The same initial history is given to
+ * every stream.  Asynchronous on `cuda_stream` (the host arrays are consumed
+ * before return).
+ */
+int32_t alz_state_init(const alz_plan* plan, double* state_dev, int64_t n_streams,
+                       const double* xinit, const double* yinit, void* cuda_stream);
+
+/* History depths (per section) of the xinit / yinit arrays above. */
+int32_t alz_plan_history(const alz_plan* plan, int32_t* xd, int32_t* yd);
+
+/*
+ * Filter a block.  x_dev: [n_streams] rows of n_samples float32, row stride
+ * x_stride elements.  y_dev: [n_streams * n_channels] rows (stream-major,
+ * channel-minor) of n_samples float32, row stride y_stride elements.
+ * state_dev: in/out, carries every recurrence across blocks, so that
+ * apply(block0) ; apply(block1) == apply(block0 ++ block1) bit for bit.
+ * Asynchronous on `cuda_stream`.
+ */
+int32_t alz_apply_f32(const alz_plan* plan, const float* x_dev, float* y_dev,
+                      double* state_dev, int64_t n_streams, int64_t n_samples,
+                      int64_t x_stride, int64_t y_stride, void* cuda_stream);
+
+/*
+ * Same with HOST buffers: host->device copy of x, the kernel, device->host copy
+ * of y, chunked over streams and pipelined on internal CUDA streams.  The host
+ * buffers may be pageable or pinned (pinned is faster).  state_dev may be NULL
+ * (zero initial state, discarded afterwards).  Synchronous: y_host is complete on
+ * return.
+ */
+int32_t alz_apply_f32_host(const alz_plan* plan, const float* x_host, float* y_host,
+                           double* state_dev, int64_t n_streams, int64_t n_samples,
+                           int64_t x_stride, int64_t y_stride);
+
+/*
+ * ParallelFilter reduction: out[s][t] = ((y[s][0][t] + y[s][1][t]) + ...) over
+ * the channel axis, left associated as reference lazy_filters.py:1053-1054.
+ * Device buffers; asynchronous on `cuda_stream`.
+ */
+int32_t alz_sum_channels_f32(const float* y_dev, float* out_dev, int64_t n_streams,
+                             int32_t n_channels, int64_t n_samples, int64_t y_stride,
+                             int64_t out_stride, void* cuda_stream);
+
+/* Number of kernel launches issued by this library since load (bench bookkeeping). */
+int64_t alz_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALZ_B200_H */
