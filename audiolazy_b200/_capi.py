@@ -1,0 +1,187 @@
+"""ctypes binding of the C ABI declared in ``include/alz_b200.h``.
+
+This is the only place Python meets native code.  There is no CPU fallback: if the
+library cannot be loaded, or a compute entry point is called without a usable CUDA
+device, a :class:`NativeError` is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _build
+
+ALZ_OK = 0
+ALZ_ERR_INVALID = -1
+ALZ_ERR_NONCAUSAL = -2
+ALZ_ERR_ZERO_GAIN = -3
+ALZ_ERR_CUDA = -4
+ALZ_ERR_NOMEM = -5
+ALZ_ERR_UNSUPPORTED = -6
+KIND_BIQUAD = 1
+KIND_GENERIC = 2
+
+#: every symbol include/alz_b200.h declares (tests check the library exports them all)
+SYMBOLS = (
+  "alz_last_error", "alz_abi_version", "alz_device_count", "alz_plan_create", "alz_plan_destroy",
+  "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
+  "alz_apply_f32_host", "alz_sum_channels_f32", "alz_launch_count",
+)
+
+
+class NativeError(RuntimeError):
+  """The native CUDA library is missing or a native call failed."""
+
+
+class PlanInfo(ctypes.Structure):
+  _fields_ = [(n, ctypes.c_int32) for n in
+              ("abi_version", "kind", "n_channels", "n_sections", "num_taps", "monic", "state_doubles", "fp64_ops",
+               "device")] + [("reserved", ctypes.c_int32 * 7)]
+
+
+_lib = None
+
+
+def lib():
+  """Load (once) ``_native/libalz_b200.so``; raise :class:`NativeError` if absent."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  path = os.environ.get("ALZ_B200_LIB", _build.LIB_PATH)
+  if not os.path.exists(path):
+    raise NativeError(
+      "audiolazy_b200 native library not found at %s -- build it with "
+      "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)" % path)
+  try:
+    L = ctypes.CDLL(path)
+  except OSError as exc:  # pragma: no cover
+    raise NativeError("cannot load %s: %s" % (path, exc))
+  i32, i64, vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+  L.alz_last_error.restype = ctypes.c_char_p
+  L.alz_last_error.argtypes = []
+  L.alz_abi_version.restype = i32
+  L.alz_device_count.restype = i32
+  L.alz_plan_create.restype = i32
+  L.alz_plan_create.argtypes = [vp, vp, i32, i32, ctypes.POINTER(vp)]
+  L.alz_plan_destroy.restype = None
+  L.alz_plan_destroy.argtypes = [vp]
+  L.alz_plan_info_get.restype = i32
+  L.alz_plan_info_get.argtypes = [vp, ctypes.POINTER(PlanInfo)]
+  L.alz_plan_state_doubles.restype = i64
+  L.alz_plan_state_doubles.argtypes = [vp, i64]
+  L.alz_state_init.restype = i32
+  L.alz_state_init.argtypes = [vp, vp, i64, vp, vp, vp]
+  L.alz_plan_history.restype = i32
+  L.alz_plan_history.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
+  L.alz_apply_f32.restype = i32
+  L.alz_apply_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
+  L.alz_apply_f32_host.restype = i32
+  L.alz_apply_f32_host.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64]
+  L.alz_sum_channels_f32.restype = i32
+  L.alz_sum_channels_f32.argtypes = [vp, vp, i64, i32, i64, i64, i64, vp]
+  L.alz_launch_count.restype = i64
+  _lib = L
+  return L
+
+
+def _check(rc):
+  if rc < 0:
+    msg = lib().alz_last_error().decode("utf-8", "replace")
+    if rc == ALZ_ERR_ZERO_GAIN:
+      raise ZeroDivisionError("Invalid filter gain")   # same exception as lazy_filters.py:177-178
+    if rc == ALZ_ERR_INVALID:
+      raise ValueError(msg)
+    raise NativeError("alz error %d: %s" % (rc, msg))
+  return rc
+
+
+def pack_sections(bank):
+  """``bank``: list (channels) of lists (sections) of ``(b, a)`` float lists ->
+  ``(coef float64[], desc int32[], C, KM)`` in the alz_plan_create layout."""
+  C = len(bank)
+  KM = max([len(ch) for ch in bank] + [1])
+  desc = np.zeros((C, KM, 3), dtype=np.int32)
+  coef = []
+  for c, ch in enumerate(bank):
+    for k, (b, a) in enumerate(ch):
+      b = [float(v) for v in b] or [0.0]
+      a = [float(v) for v in a]
+      desc[c, k] = (len(b), len(a), len(coef))
+      coef.extend(b)
+      coef.extend(a)
+  return np.asarray(coef or [0.0], dtype=np.float64), np.ascontiguousarray(desc.reshape(-1)), C, KM
+
+
+class Plan(object):
+  """A compiled bank of cascades living on the current CUDA device."""
+
+  def __init__(self, bank):
+    L = lib()
+    coef, desc, C, KM = pack_sections(bank)
+    handle = ctypes.c_void_p()
+    _check(L.alz_plan_create(coef.ctypes.data, desc.ctypes.data, C, KM, ctypes.byref(handle)))
+    self._h = handle
+    info = PlanInfo()
+    _check(L.alz_plan_info_get(self._h, ctypes.byref(info)))
+    self.kind = info.kind
+    self.n_channels = info.n_channels
+    self.n_sections = info.n_sections
+    self.num_taps = info.num_taps
+    self.monic = bool(info.monic)
+    self.state_doubles_per_recurrence = info.state_doubles
+    self.fp64_ops = info.fp64_ops
+    self.device = info.device
+    xd, yd = ctypes.c_int32(), ctypes.c_int32()
+    _check(L.alz_plan_history(self._h, ctypes.byref(xd), ctypes.byref(yd)))
+    self.xd, self.yd = xd.value, yd.value
+
+  def __del__(self):
+    h, self._h = getattr(self, "_h", None), None
+    if h and _lib is not None:
+      _lib.alz_plan_destroy(h)
+
+  def state_doubles(self, n_streams):
+    return _check(lib().alz_plan_state_doubles(self._h, int(n_streams)))
+
+  def state_init(self, state_ptr, n_streams, xinit=None, yinit=None, stream=0):
+    xi = None if xinit is None else np.ascontiguousarray(xinit, dtype=np.float64)
+    yi = None if yinit is None else np.ascontiguousarray(yinit, dtype=np.float64)
+    for arr, depth in ((xi, self.xd), (yi, self.yd)):
+      if arr is not None and arr.size != self.n_channels * self.n_sections * depth:
+        raise ValueError("initial history must have shape [%d][%d][%d]" % (self.n_channels, self.n_sections, depth))
+    _check(lib().alz_state_init(self._h, state_ptr, int(n_streams),
+                                None if xi is None else xi.ctypes.data,
+                                None if yi is None else yi.ctypes.data, stream))
+
+  def apply(self, x_ptr, y_ptr, state_ptr, n_streams, n_samples, x_stride, y_stride, stream=0):
+    _check(lib().alz_apply_f32(self._h, x_ptr, y_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),
+                               int(y_stride), stream))
+
+  def apply_host(self, x, y=None, state_ptr=None):
+    """``x``: float32 ndarray [S][T] (C-contiguous rows). Returns ``y`` [S][C][T]."""
+    x = np.asarray(x, dtype=np.float32)
+    if x.ndim == 1:
+      x = x[None, :]
+    if x.strides[1] != 4:
+      x = np.ascontiguousarray(x)
+    S, T = x.shape
+    if y is None:
+      y = np.empty((S, self.n_channels, T), dtype=np.float32)
+    assert y.dtype == np.float32 and y.shape == (S, self.n_channels, T) and y.flags.c_contiguous
+    _check(lib().alz_apply_f32_host(self._h, x.ctypes.data, y.ctypes.data, state_ptr, S, T, x.strides[0] // 4, T))
+    return y
+
+
+def sum_channels(y_ptr, out_ptr, n_streams, n_channels, n_samples, y_stride, out_stride, stream=0):
+  _check(lib().alz_sum_channels_f32(y_ptr, out_ptr, int(n_streams), int(n_channels), int(n_samples), int(y_stride),
+                                    int(out_stride), stream))
+
+
+def device_count():
+  return lib().alz_device_count()
+
+
+def launch_count():
+  return lib().alz_launch_count()

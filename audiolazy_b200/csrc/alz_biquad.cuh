@@ -1,0 +1,164 @@
+// alz_biquad.cuh -- cascade-of-biquads recurrence core (the hot kernel).
+//
+// Math (reference LinearFilter.__call__, lazy_filters.py:197-257, composed by
+// CascadeFilter.__call__, :988-990).  Section k of a cascade computes
+//     u_k[n] = (b0 u_{k-1}[n] + b1 u_{k-1}[n-1] + b2 u_{k-1}[n-2]
+//               - a1 u_k[n-1] - a2 u_k[n-2]) / a0 ,      u_0 = x,  y = u_K.
+// The reference evaluates this in float64 with separately rounded products.  Here:
+//   * the whole cascade stays in FLOAT64 REGISTERS (state) and UNIFORM REGISTERS
+//     (coefficients); float32 exists only in HBM and in the shared-memory tile.
+//     float32 coefficients/state miss the 1e-5 parity bar by up to
+//     6 orders of magnitude on low ERB channels.
+//   * a0 is folded into the coefficients on the host, products are fused (DFMA).
+//   * MONIC form: b0 of every section is factored out (floating point is scale
+//     invariant, so this costs no accuracy): in working units u'_k = u_k * sc_k with
+//     sc_k = 1/(b0_1...b0_k),
+//         u'_k[n] = u'_{k-1}[n] + c1 u'_{k-1}[n-1] + c2 u'_{k-1}[n-2]
+//                   + na1 u'_k[n-1] + na2 u'_k[n-2]          (NB-1+2 DFMA)
+//     and y = G * u'_K with G = b0_1...b0_K (one DMUL).  For the gammatone "slaney"
+//     cascade (4 sections, 2 numerator taps): 4*3 + 1 = 13 FP64 ops per
+//     channel-sample instead of the reference's 28 flops / 16 fused ops.
+//   * once two samples have been processed, the input history of section k IS the
+//     output history of section k-1, so the steady-state loop keeps only K+1 signal
+//     histories (aliased form).  The first two samples of every launch use explicit
+//     per-section input histories so that memory=/zero= seeding
+//     (lazy_filters.py:181-195, :243-250) is honoured exactly; when the state comes
+//     from a previous launch the two forms see identical operands, so splitting a
+//     stream into blocks is bit-exact.
+//   * the state buffer holds WORKING-unit values (the host scales memory=/zero= once
+//     in alz_state_init), so no rounding happens at block boundaries.
+//
+// Cost model (B200, measured): DFMA/DMUL with a uniform-register coefficient = 2.06
+// cycles per warp per SM sub-partition, F2F (either direction) ~4.  Slaney bank:
+// 13 x 2.06 + 2 x 4 = ~35 cycles per warp-sample: the kernel is FP64-issue bound below
+// the HBM roofline, by construction of the arithmetic the parity bar demands.
+#pragma once
+#include "alz_lane.cuh"
+
+#ifndef ALZ_GROUP_UNROLL
+#define ALZ_GROUP_UNROLL 2   // groups of 4 samples unrolled in the steady-state loop
+#endif
+constexpr int kAlzGroupUnroll = ALZ_GROUP_UNROLL;
+
+// Per-channel coefficient record inside the kernel parameters (constant bank):
+//   [k*5 + 0..4] = b0 (1 when monic), b1|c1, b2|c2, -a1, -a2   (all / a0);  [5K] = G.
+#define ALZ_COEF_STRIDE(K) (5 * (K) + 1)
+// State: state[slot * sstride + r], r = s*C + c, slots 4k+0..3 = xd1, xd2, yd1, yd2 of
+// section k (working units).
+template <int NCOEF>
+struct AlzBiquadArgs {
+  double* state;
+  long long sstride;   // slot stride of the state buffer (recurrences it was sized for)
+  double coef[NCOEF];  // [channels of this launch][ALZ_COEF_STRIDE(K)]
+};
+
+template <int K, int NB, bool MONIC>
+struct AlzBiquadCore {
+  double b0[K], c1[K], c2[K], na1[K], na2[K];
+  double G;
+  double u[K + 1][2];   // u[k][0] = u_k[n-1], u[k][1] = u_k[n-2]  (working units)
+  double xe[K][2];      // explicit input histories of sections 1..K-1 (index 0 unused)
+
+  template <class Args>
+  __device__ __forceinline__ void load(const Args& ca, long long r, int c_local, bool /*valid*/) {
+    const double* cf = ca.coef + c_local * ALZ_COEF_STRIDE(K);   // CTA-uniform address
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      b0[k] = cf[5 * k + 0];
+      c1[k] = cf[5 * k + 1];
+      c2[k] = cf[5 * k + 2];
+      na1[k] = cf[5 * k + 3];
+      na2[k] = cf[5 * k + 4];
+    }
+    G = cf[5 * K];
+    const double* st = ca.state + r;
+    const long long R = ca.sstride;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double x1 = st[(4 * k + 0) * R], x2 = st[(4 * k + 1) * R];
+      if (k == 0) { u[0][0] = x1; u[0][1] = x2; xe[0][0] = xe[0][1] = 0.0; }
+      else { xe[k][0] = x1; xe[k][1] = x2; }
+      u[k + 1][0] = st[(4 * k + 2) * R];
+      u[k + 1][1] = st[(4 * k + 3) * R];
+    }
+  }
+
+  // One section's arithmetic.  in/in1/in2 = u_{k-1}[n], [n-1], [n-2].
+  __device__ __forceinline__ double section(int k, double in, double in1, double in2, double y1, double y2) const {
+    double t = MONIC ? in : b0[k] * in;
+    if (NB >= 2) t = fma(c1[k], in1, t);
+    if (NB >= 3) t = fma(c2[k], in2, t);
+    t = fma(na2[k], y2, t);
+    return fma(na1[k], y1, t);
+  }
+
+  // Steady state: section k reads the history of section k-1's output.
+  __device__ __forceinline__ float step_alias(double xin) {
+    double in = xin, in1 = u[0][0], in2 = u[0][1];
+    u[0][1] = in1;
+    u[0][0] = in;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const double y1 = u[k + 1][0], y2 = u[k + 1][1];
+      const double y = section(k, in, in1, in2, y1, y2);
+      u[k + 1][1] = y1;
+      u[k + 1][0] = y;
+      in = y; in1 = y1; in2 = y2;
+    }
+    return (float)(MONIC ? G * in : in);
+  }
+
+  // First two samples of a launch: explicit input histories.
+  __device__ __forceinline__ float step_explicit(double xin) {
+    double in = xin;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double in1, in2;
+      if (k == 0) { in1 = u[0][0]; in2 = u[0][1]; u[0][1] = in1; u[0][0] = in; }
+      else { in1 = xe[k][0]; in2 = xe[k][1]; xe[k][1] = in1; xe[k][0] = in; }
+      const double y1 = u[k + 1][0], y2 = u[k + 1][1];
+      const double y = section(k, in, in1, in2, y1, y2);
+      u[k + 1][1] = y1;
+      u[k + 1][0] = y;
+      in = y;
+    }
+    return (float)(MONIC ? G * in : in);
+  }
+
+  // Filter my row of the tile in place: float32 in, float32 out.
+  __device__ __forceinline__ void tile(float* row, int nvalid, long long n_done) {
+    if (nvalid == ALZ_TT && n_done >= 2) {
+#pragma unroll kAlzGroupUnroll
+      for (int g = 0; g < ALZ_TT / 4; ++g) {
+        const float4 xf = *reinterpret_cast<const float4*>(row + 4 * g);
+        float4 o;
+        o.x = step_alias((double)xf.x);
+        o.y = step_alias((double)xf.y);
+        o.z = step_alias((double)xf.z);
+        o.w = step_alias((double)xf.w);
+        *reinterpret_cast<float4*>(row + 4 * g) = o;
+      }
+    } else {
+      for (int j = 0; j < nvalid; ++j) {
+        const double xin = (double)row[j];
+        row[j] = (n_done + j < 2) ? step_explicit(xin) : step_alias(xin);
+      }
+    }
+  }
+
+  template <class Args>
+  __device__ __forceinline__ void store(const Args& ca, long long r, long long T) {
+    double* st = ca.state + r;
+    const long long R = ca.sstride;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      double x1, x2;
+      if (k == 0 || T >= 2) { x1 = u[k][0]; x2 = u[k][1]; }   // aliased (or the input itself)
+      else { x1 = xe[k][0]; x2 = xe[k][1]; }
+      st[(4 * k + 0) * R] = x1;
+      st[(4 * k + 1) * R] = x2;
+      st[(4 * k + 2) * R] = u[k + 1][0];
+      st[(4 * k + 3) * R] = u[k + 1][1];
+    }
+  }
+};

@@ -1,0 +1,575 @@
+// alz_capi.cu -- the C ABI of include/alz_b200.h: plan building, state seeding,
+// kernel dispatch and the host-buffer pipeline.  No torch types, no CPU compute path.
+#include "../../include/alz_b200.h"
+#include "alz_biquad.cuh"
+#include "alz_generic.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// ----------------------------------------------------------------------------------
+// error plumbing
+// ----------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define ALZ_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(ALZ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// ----------------------------------------------------------------------------------
+// plan
+// ----------------------------------------------------------------------------------
+struct HostPipe {   // lazily created resources of alz_apply_f32_host
+  static const int NBUF = 3;
+  cudaStream_t stream[NBUF] = {nullptr, nullptr, nullptr};
+  float* dx[NBUF] = {nullptr, nullptr, nullptr};
+  float* dy[NBUF] = {nullptr, nullptr, nullptr};
+  size_t dx_bytes = 0, dy_bytes = 0;
+  bool ready = false;
+};
+
+struct alz_plan {
+  int kind = 0, C = 0, K = 0, NB = 0, monic = 0, device = 0;
+  int xd = 0, yd = 0;          // history depths exposed to alz_state_init
+  int state_doubles = 0;       // per recurrence
+  int fp64_ops = 0;
+  // device tables
+  double* d_coef = nullptr;
+  AlzGenSection* d_sec = nullptr;
+  int* d_tap_delay = nullptr;
+  // host copies used by alz_state_init
+  std::vector<double> h_tab;              // biquad: [C][5K+1] coefficient records (kernel parameters)
+  std::vector<double> sc;                 // biquad: [C][K+1] working-unit scales
+  std::vector<AlzGenSection> h_sec;       // generic
+  std::vector<int> h_xlen, h_ylen;        // generic: true max delays per section
+  std::mutex host_mu;
+  HostPipe pipe;
+};
+
+// Kernel-parameter coefficient capacity (doubles).  CUDA 12.1+ allows 32764 bytes of
+// parameters; two sizes so that small filters do not push 28 KB per launch.
+static const int kCoefSmall = 512, kCoefLarge = 3584;
+static const int kWarpsPerSm = 22;   // 2 x 4608 B tile buffers + 1 KB CTA reserve -> 22 CTAs per SM
+
+template <int K, int NB, bool MONIC, int NCOEF>
+__global__ void __launch_bounds__(32, kWarpsPerSm)
+alz_biquad_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca) {
+  extern __shared__ __align__(16) float alz_smem[];
+  alz_run_warp<AlzBiquadCore<K, NB, MONIC>>(a, ca, alz_smem);
+}
+
+__global__ void __launch_bounds__(32)
+alz_generic_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzGenericArgs ca) {
+  extern __shared__ __align__(16) float alz_smem[];
+  alz_run_warp<AlzGenericCore>(a, ca, alz_smem);
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// One launch: channels [c0, c0+nch) x stream groups of `ta` (ta.S <= 65535*32 streams).
+template <int K, int NB, bool MONIC, int NCOEF>
+static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, int c0, int nch,
+                               cudaStream_t st) {
+  static AlzBiquadArgs<NCOEF> ca;   // too large for the stack of some callers; filled under a lock
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  ca.state = state;
+  ca.sstride = sstride;
+  const int stride = ALZ_COEF_STRIDE(K);
+  memcpy(ca.coef, p->h_tab.data() + (size_t)c0 * stride, (size_t)nch * stride * sizeof(double));
+  ta.c_base = c0;
+  const long long groups = (ta.S + 31) / 32;
+  auto kern = alz_biquad_kernel<K, NB, MONIC, NCOEF>;
+  kern<<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
+  ALZ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ALZ_OK;
+}
+
+template <int K, int NB, bool MONIC>
+static int launch_biquad_t(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
+  const int stride = ALZ_COEF_STRIDE(K);
+  const bool small = p->C * stride <= kCoefSmall;
+  const int per_launch = (small ? kCoefSmall : kCoefLarge) / stride;
+  for (int c0 = 0; c0 < p->C; c0 += per_launch) {
+    const int nch = std::min(per_launch, p->C - c0);
+    const int rc = small ? launch_biquad_chunk<K, NB, MONIC, kCoefSmall>(p, ta, state, sstride, c0, nch, st)
+                         : launch_biquad_chunk<K, NB, MONIC, kCoefLarge>(p, ta, state, sstride, c0, nch, st);
+    if (rc != ALZ_OK) return rc;
+  }
+  return ALZ_OK;
+}
+
+template <int K, int NB>
+static int launch_biquad_nb(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
+  if (p->monic) return launch_biquad_t<K, NB, true>(p, ta, state, sstride, st);
+  return launch_biquad_t<K, NB, false>(p, ta, state, sstride, st);
+}
+template <int K>
+static int launch_biquad_k(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
+  switch (p->NB) {
+    case 1: return launch_biquad_nb<K, 1>(p, ta, state, sstride, st);
+    case 2: return launch_biquad_nb<K, 2>(p, ta, state, sstride, st);
+    default: return launch_biquad_nb<K, 3>(p, ta, state, sstride, st);
+  }
+}
+static int launch_biquad(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
+  switch (p->K) {
+    case 1: return launch_biquad_k<1>(p, ta, state, sstride, st);
+    case 2: return launch_biquad_k<2>(p, ta, state, sstride, st);
+    case 3: return launch_biquad_k<3>(p, ta, state, sstride, st);
+    case 4: return launch_biquad_k<4>(p, ta, state, sstride, st);
+    case 6: return launch_biquad_k<6>(p, ta, state, sstride, st);
+    case 8: return launch_biquad_k<8>(p, ta, state, sstride, st);
+  }
+  return fail(ALZ_ERR_UNSUPPORTED, "no biquad kernel for K=%d", p->K);
+}
+
+static int launch_generic(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, cudaStream_t st) {
+  AlzGenericArgs ga{p->d_sec, p->d_tap_delay, p->d_coef, state, sstride, p->K, p->C, 0};
+  ta.c_base = 0;
+  const long long groups = (ta.S + 31) / 32;
+  alz_generic_kernel<<<dim3((unsigned)p->C, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ga);
+  ALZ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ALZ_OK;
+}
+
+static const int kBiquadKs[] = {1, 2, 3, 4, 6, 8};
+
+// ----------------------------------------------------------------------------------
+extern "C" {
+
+const char* alz_last_error(void) { return g_err.c_str(); }
+int32_t alz_abi_version(void) { return ALZ_ABI_VERSION; }
+int64_t alz_launch_count(void) { return g_launches.load(); }
+
+int32_t alz_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int32_t KM, alz_plan** out) {
+  if (!out) return fail(ALZ_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!coef || !desc || C <= 0 || KM < 0) return fail(ALZ_ERR_INVALID, "bad plan arguments");
+  int dev = 0;
+  ALZ_CUDA(cudaGetDevice(&dev));
+
+  // ---- normalise every section: divide by a0, trim trailing zeros ------------------
+  struct Sec { std::vector<double> b, a; };   // a[0] == 1 after normalisation (kept for indexing)
+  std::vector<std::vector<Sec>> secs(C);
+  int Kmax = 0, nbmax = 1, namax = 1;
+  for (int c = 0; c < C; ++c) {
+    bool ended = false;
+    for (int k = 0; k < KM; ++k) {
+      const int32_t* d = desc + ((size_t)c * KM + k) * 3;
+      const int nb = d[0], na = d[1];
+      if (nb == 0) { ended = true; continue; }
+      if (ended) return fail(ALZ_ERR_INVALID, "channel %d: section %d follows an absent section", c, k);
+      if (nb < 0 || na < 1 || d[2] < 0) return fail(ALZ_ERR_INVALID, "channel %d section %d: bad descriptor", c, k);
+      const double* b = coef + d[2];
+      const double* a = b + nb;
+      if (a[0] == 0.0) return fail(ALZ_ERR_ZERO_GAIN, "channel %d section %d: Invalid filter gain (a0 == 0)", c, k);
+      Sec s;
+      s.b.assign(b, b + nb);
+      s.a.assign(a, a + na);
+      const double a0 = a[0];
+      if (a0 != 1.0) {
+        for (auto& v : s.b) v /= a0;
+        for (auto& v : s.a) v /= a0;
+        s.a[0] = 1.0;
+      }
+      while (s.b.size() > 1 && s.b.back() == 0.0) s.b.pop_back();
+      while (s.a.size() > 1 && s.a.back() == 0.0) s.a.pop_back();
+      for (double v : s.b) if (!std::isfinite(v)) return fail(ALZ_ERR_INVALID, "non-finite coefficient");
+      for (double v : s.a) if (!std::isfinite(v)) return fail(ALZ_ERR_INVALID, "non-finite coefficient");
+      nbmax = std::max(nbmax, (int)s.b.size());
+      namax = std::max(namax, (int)s.a.size());
+      secs[c].push_back(std::move(s));
+    }
+    Kmax = std::max(Kmax, (int)secs[c].size());
+  }
+  if (Kmax == 0) Kmax = 1;   // bank of empty cascades: identity
+
+  alz_plan* p = new (std::nothrow) alz_plan();
+  if (!p) return fail(ALZ_ERR_NOMEM, "out of host memory");
+  p->C = C;
+  p->device = dev;
+
+  const bool biquad = nbmax <= 3 && namax <= 3 && Kmax <= 8;
+  if (biquad) {
+    int K = 8;
+    for (int kk : kBiquadKs) if (kk >= Kmax) { K = kk; break; }
+    p->kind = ALZ_KIND_BIQUAD;
+    p->K = K;
+    p->NB = nbmax;
+    p->xd = 2; p->yd = 2;
+    p->state_doubles = 4 * K;
+    // monic only if every b0 is a normal number and the running products stay normal
+    bool monic = true;
+    for (int c = 0; c < C && monic; ++c) {
+      double g = 1.0;
+      for (auto& s : secs[c]) {
+        const double b0 = s.b[0];
+        if (!(std::fabs(b0) > 1e-150 && std::fabs(b0) < 1e150)) { monic = false; break; }
+        g *= b0;
+        if (!(std::fabs(g) > 1e-250 && std::fabs(g) < 1e250)) { monic = false; break; }
+      }
+    }
+    p->monic = monic ? 1 : 0;
+    p->fp64_ops = monic ? K * (p->NB - 1 + 2) + 1 : K * (p->NB + 2);
+    const int stride = ALZ_COEF_STRIDE(K);
+    p->h_tab.assign((size_t)C * stride, 0.0);
+    p->sc.assign((size_t)C * (K + 1), 1.0);
+    for (int c = 0; c < C; ++c) {
+      double* rec = p->h_tab.data() + (size_t)c * stride;
+      double g = 1.0, sc = 1.0;
+      for (int k = 0; k < K; ++k) {
+        double b[3] = {1.0, 0.0, 0.0}, a[3] = {1.0, 0.0, 0.0};   // identity padding
+        if (k < (int)secs[c].size()) {
+          const Sec& s = secs[c][k];
+          b[0] = 0.0;
+          for (size_t i = 0; i < s.b.size(); ++i) b[i] = s.b[i];
+          for (size_t i = 0; i < s.a.size(); ++i) a[i] = s.a[i];
+        }
+        if (monic) {
+          rec[5 * k + 0] = 1.0;
+          rec[5 * k + 1] = b[1] / b[0];
+          rec[5 * k + 2] = b[2] / b[0];
+          g *= b[0];
+          sc /= b[0];
+        } else {
+          rec[5 * k + 0] = b[0];
+          rec[5 * k + 1] = b[1];
+          rec[5 * k + 2] = b[2];
+        }
+        rec[5 * k + 3] = -a[1];
+        rec[5 * k + 4] = -a[2];
+        p->sc[(size_t)c * (K + 1) + k + 1] = sc;
+      }
+      rec[5 * K] = monic ? g : 1.0;
+    }
+  } else {
+    // ---- generic: union tap structure per section --------------------------------
+    const int K = Kmax;
+    p->kind = ALZ_KIND_GENERIC;
+    p->K = K;
+    p->NB = nbmax;
+    p->monic = 0;
+    std::vector<int> tap_delay;
+    std::vector<std::vector<double>> tap_coef;   // [tap][C]
+    p->h_sec.resize(K);
+    p->h_xlen.assign(K, 0);
+    p->h_ylen.assign(K, 0);
+    int slot = 1;   // slot 0: absolute sample count
+    int ops = 0, xdmax = 0, ydmax = 0;
+    for (int k = 0; k < K; ++k) {
+      size_t nb = 1, na = 1;
+      for (int c = 0; c < C; ++c)
+        if (k < (int)secs[c].size()) { nb = std::max(nb, secs[c][k].b.size()); na = std::max(na, secs[c][k].a.size()); }
+      AlzGenSection gs{};
+      gs.num_begin = (int)tap_delay.size();
+      for (size_t d = 0; d < nb; ++d) {
+        std::vector<double> col(C, 0.0);
+        bool any = false;
+        for (int c = 0; c < C; ++c) {
+          double v;
+          if (k < (int)secs[c].size()) v = d < secs[c][k].b.size() ? secs[c][k].b[d] : 0.0;
+          else v = d == 0 ? 1.0 : 0.0;   // identity padding
+          col[c] = v;
+          any = any || v != 0.0;
+        }
+        if (any || d == 0) { tap_delay.push_back((int)d); tap_coef.push_back(std::move(col)); }
+      }
+      gs.nnum = (int)tap_delay.size() - gs.num_begin;
+      gs.den_begin = (int)tap_delay.size();
+      for (size_t d = 1; d < na; ++d) {
+        std::vector<double> col(C, 0.0);
+        bool any = false;
+        for (int c = 0; c < C; ++c) {
+          double v = (k < (int)secs[c].size() && d < secs[c][k].a.size()) ? -secs[c][k].a[d] : 0.0;
+          col[c] = v;
+          any = any || v != 0.0;
+        }
+        if (any) { tap_delay.push_back((int)d); tap_coef.push_back(std::move(col)); }
+      }
+      gs.nden = (int)tap_delay.size() - gs.den_begin;
+      const int xlen = (int)nb - 1, ylen = (int)na - 1;
+      auto pow2 = [](int n) { int q = 1; while (q < n) q <<= 1; return q; };
+      if (xlen > 0) { gs.xbase = slot; gs.xmask = pow2(xlen) - 1; slot += gs.xmask + 1; } else { gs.xbase = 0; gs.xmask = -1; }
+      if (ylen > 0) { gs.ybase = slot; gs.ymask = pow2(ylen) - 1; slot += gs.ymask + 1; } else { gs.ybase = 0; gs.ymask = -1; }
+      p->h_sec[k] = gs;
+      p->h_xlen[k] = xlen;
+      p->h_ylen[k] = ylen;
+      xdmax = std::max(xdmax, xlen);
+      ydmax = std::max(ydmax, ylen);
+      ops += gs.nnum + gs.nden;
+    }
+    p->xd = xdmax; p->yd = ydmax;
+    p->state_doubles = slot;
+    p->fp64_ops = ops;
+    const size_t ntaps = tap_delay.size();
+    std::vector<double> tab(ntaps * C);
+    for (size_t t = 0; t < ntaps; ++t) memcpy(&tab[t * C], tap_coef[t].data(), C * sizeof(double));
+    cudaError_t e = cudaMalloc(&p->d_coef, tab.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_coef, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_sec, K * sizeof(AlzGenSection));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_sec, p->h_sec.data(), K * sizeof(AlzGenSection), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_tap_delay, ntaps * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_tap_delay, tap_delay.data(), ntaps * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { alz_plan_destroy(p); return fail(ALZ_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e)); }
+  }
+  *out = p;
+  return ALZ_OK;
+}
+
+void alz_plan_destroy(alz_plan* p) {
+  if (!p) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(p->device);
+  if (p->pipe.ready) {
+    for (int i = 0; i < HostPipe::NBUF; ++i) {
+      if (p->pipe.stream[i]) { cudaStreamSynchronize(p->pipe.stream[i]); cudaStreamDestroy(p->pipe.stream[i]); }
+      cudaFree(p->pipe.dx[i]);
+      cudaFree(p->pipe.dy[i]);
+    }
+  }
+  cudaFree(p->d_coef);
+  cudaFree(p->d_sec);
+  cudaFree(p->d_tap_delay);
+  cudaSetDevice(cur);
+  cudaGetLastError();
+  delete p;
+}
+
+int32_t alz_plan_info_get(const alz_plan* p, alz_plan_info* out) {
+  if (!p || !out) return fail(ALZ_ERR_INVALID, "null argument");
+  memset(out, 0, sizeof *out);
+  out->abi_version = ALZ_ABI_VERSION;
+  out->kind = p->kind;
+  out->n_channels = p->C;
+  out->n_sections = p->K;
+  out->num_taps = p->NB;
+  out->monic = p->monic;
+  out->state_doubles = p->state_doubles;
+  out->fp64_ops = p->fp64_ops;
+  out->device = p->device;
+  return ALZ_OK;
+}
+
+int64_t alz_plan_state_doubles(const alz_plan* p, int64_t S) {
+  if (!p || S < 0) return fail(ALZ_ERR_INVALID, "bad argument");
+  return (int64_t)p->state_doubles * S * p->C;
+}
+
+int32_t alz_plan_history(const alz_plan* p, int32_t* xd, int32_t* yd) {
+  if (!p || !xd || !yd) return fail(ALZ_ERR_INVALID, "null argument");
+  *xd = p->xd;
+  *yd = p->yd;
+  return ALZ_OK;
+}
+
+// Broadcast one per-channel row of slot values to all streams: state[slot*R + s*C + c].
+__global__ void alz_state_fill_kernel(double* state, const double* proto, long long R, int C, int slots) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * slots) return;
+  const long long slot = i / R, r = i - slot * R;
+  state[i] = proto[slot * C + (int)(r % C)];
+}
+
+int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double* xinit, const double* yinit,
+                       void* cuda_stream) {
+  if (!p || S < 0) return fail(ALZ_ERR_INVALID, "bad argument");
+  if (S == 0) return ALZ_OK;
+  if (!state) return fail(ALZ_ERR_INVALID, "state is null");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const long long R = (long long)S * p->C;
+  const size_t bytes = (size_t)p->state_doubles * R * sizeof(double);
+  if (!xinit && !yinit) {
+    ALZ_CUDA(cudaMemsetAsync(state, 0, bytes, st));
+    return ALZ_OK;
+  }
+  const int C = p->C, K = p->K, slots = p->state_doubles;
+  std::vector<double> proto((size_t)slots * C, 0.0);
+  if (p->kind == ALZ_KIND_BIQUAD) {
+    for (int c = 0; c < C; ++c)
+      for (int k = 0; k < K; ++k) {
+        const double sc_in = p->sc[(size_t)c * (K + 1) + k], sc_out = p->sc[(size_t)c * (K + 1) + k + 1];
+        for (int j = 0; j < 2; ++j) {
+          const double xv = xinit ? xinit[((size_t)c * K + k) * 2 + j] : 0.0;
+          const double yv = yinit ? yinit[((size_t)c * K + k) * 2 + j] : 0.0;
+          proto[(size_t)(4 * k + j) * C + c] = xv * sc_in;
+          proto[(size_t)(4 * k + 2 + j) * C + c] = yv * sc_out;
+        }
+      }
+  } else {
+    for (int c = 0; c < C; ++c)
+      for (int k = 0; k < K; ++k) {
+        const AlzGenSection& gs = p->h_sec[k];
+        for (int j = 0; j < p->h_xlen[k]; ++j) {   // delay j+1 lives at ring position (-(j+1)) & mask
+          const double xv = xinit ? xinit[((size_t)c * K + k) * p->xd + j] : 0.0;
+          proto[(size_t)(gs.xbase + ((-(j + 1)) & gs.xmask)) * C + c] = xv;
+        }
+        for (int j = 0; j < p->h_ylen[k]; ++j) {
+          const double yv = yinit ? yinit[((size_t)c * K + k) * p->yd + j] : 0.0;
+          proto[(size_t)(gs.ybase + ((-(j + 1)) & gs.ymask)) * C + c] = yv;
+        }
+      }
+  }
+  double* d_proto = nullptr;
+  ALZ_CUDA(cudaMallocAsync((void**)&d_proto, proto.size() * sizeof(double), st));
+  ALZ_CUDA(cudaMemcpyAsync(d_proto, proto.data(), proto.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  const long long n = R * slots;
+  alz_state_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(state, d_proto, R, C, slots);
+  ALZ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  ALZ_CUDA(cudaFreeAsync(d_proto, st));
+  ALZ_CUDA(cudaStreamSynchronize(st));   // proto (pageable host vector) must be consumed before return
+  return ALZ_OK;
+}
+
+static int apply_impl(const alz_plan* p, const float* x, float* y, double* state, long long sstride, long long S,
+                      long long T, long long xs, long long ys, cudaStream_t st) {
+  AlzTileArgs ta{};
+  ta.T = T; ta.xs = xs; ta.ys = ys; ta.C = p->C; ta.c_base = 0;
+  ta.vec_in = (((uintptr_t)x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
+  ta.vec_out = (((uintptr_t)y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
+  const long long kMaxStreams = 65535ll * 32;   // gridDim.y limit
+  for (long long s0 = 0; s0 < S; s0 += kMaxStreams) {
+    ta.S = std::min(kMaxStreams, S - s0);
+    ta.x = x + s0 * xs;
+    ta.y = y + s0 * p->C * ys;
+    double* stp = state + s0 * p->C;
+    const int rc = p->kind == ALZ_KIND_BIQUAD ? launch_biquad(p, ta, stp, sstride, st)
+                                               : launch_generic(p, ta, stp, sstride, st);
+    if (rc != ALZ_OK) return rc;
+  }
+  return ALZ_OK;
+}
+
+int32_t alz_apply_f32(const alz_plan* p, const float* x, float* y, double* state, int64_t S, int64_t T,
+                      int64_t xs, int64_t ys, void* cuda_stream) {
+  if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (S < 0 || T < 0) return fail(ALZ_ERR_INVALID, "negative size");
+  if (S == 0 || T == 0) return ALZ_OK;
+  if (!x || !y || !state) return fail(ALZ_ERR_INVALID, "null buffer");
+  if (xs < T || ys < T) return fail(ALZ_ERR_INVALID, "row stride shorter than n_samples");
+  return apply_impl(p, x, y, state, (long long)S * p->C, S, T, xs, ys, (cudaStream_t)cuda_stream);
+}
+
+int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, double* state, int64_t S, int64_t T,
+                           int64_t xs, int64_t ys) {
+  alz_plan* p = const_cast<alz_plan*>(cp);
+  if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (S < 0 || T < 0) return fail(ALZ_ERR_INVALID, "negative size");
+  if (S == 0 || T == 0) return ALZ_OK;
+  if (!xh || !yh) return fail(ALZ_ERR_INVALID, "null buffer");
+  if (xs < T || ys < T) return fail(ALZ_ERR_INVALID, "row stride shorter than n_samples");
+  std::lock_guard<std::mutex> lock(p->host_mu);
+  ALZ_CUDA(cudaSetDevice(p->device));
+  HostPipe& hp = p->pipe;
+  const long long C = p->C;
+  const long long Tp = (T + 3) & ~3LL;   // device row pitch: keeps every row 16-byte aligned
+  // chunk over streams: <= 128 MiB of output per chunk, at least 1 stream
+  long long Sc = (128LL << 20) / (C * Tp * 4);
+  if (Sc < 1) Sc = 1;
+  if (Sc > S) Sc = S;
+  const size_t need_x = (size_t)Sc * Tp * 4, need_y = (size_t)Sc * C * Tp * 4;
+  if (!hp.ready) {
+    for (int i = 0; i < HostPipe::NBUF; ++i) ALZ_CUDA(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
+    hp.ready = true;
+  }
+  if (hp.dx_bytes < need_x || hp.dy_bytes < need_y) {
+    for (int i = 0; i < HostPipe::NBUF; ++i) {
+      ALZ_CUDA(cudaStreamSynchronize(hp.stream[i]));
+      cudaFree(hp.dx[i]); hp.dx[i] = nullptr;
+      cudaFree(hp.dy[i]); hp.dy[i] = nullptr;
+    }
+    hp.dx_bytes = hp.dy_bytes = 0;
+    for (int i = 0; i < HostPipe::NBUF; ++i) {
+      ALZ_CUDA(cudaMalloc(&hp.dx[i], need_x));
+      ALZ_CUDA(cudaMalloc(&hp.dy[i], need_y));
+    }
+    hp.dx_bytes = need_x;
+    hp.dy_bytes = need_y;
+  }
+  double* st_buf = state;
+  bool own_state = false;
+  if (!st_buf) {
+    ALZ_CUDA(cudaMalloc(&st_buf, (size_t)p->state_doubles * S * C * sizeof(double)));
+    own_state = true;
+    ALZ_CUDA(cudaMemsetAsync(st_buf, 0, (size_t)p->state_doubles * S * C * sizeof(double), hp.stream[0]));
+    ALZ_CUDA(cudaStreamSynchronize(hp.stream[0]));
+  }
+  int rc = ALZ_OK;
+  int i = 0;
+  for (long long s0 = 0; s0 < S && rc == ALZ_OK; s0 += Sc, ++i) {
+    const int b = i % HostPipe::NBUF;
+    const long long n = std::min<long long>(Sc, S - s0);
+    cudaStream_t st = hp.stream[b];
+    cudaError_t e = cudaMemcpy2DAsync(hp.dx[b], Tp * 4, xh + s0 * xs, xs * 4, T * 4, n, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+    rc = apply_impl(p, hp.dx[b], hp.dy[b], st_buf + s0 * C, (long long)S * C, n, T, Tp, Tp, st);
+    if (rc != ALZ_OK) break;
+    e = cudaMemcpy2DAsync(yh + s0 * C * ys, ys * 4, hp.dy[b], Tp * 4, T * 4, n * C, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
+  }
+  for (int k = 0; k < HostPipe::NBUF; ++k) {
+    cudaError_t e = cudaStreamSynchronize(hp.stream[k]);
+    if (e != cudaSuccess && rc == ALZ_OK) rc = fail(ALZ_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
+  }
+  if (own_state) cudaFree(st_buf);
+  return rc;
+}
+
+__global__ void alz_sum_channels_kernel(const float* y, float* out, long long S, int C, long long T, long long ys,
+                                        long long os) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * T) return;
+  const long long s = i / T, t = i - s * T;
+  const float* row = y + (s * C) * ys + t;
+  double acc = row[0];
+  for (int c = 1; c < C; ++c) acc += (double)row[(long long)c * ys];
+  out[s * os + t] = (float)acc;
+}
+
+int32_t alz_sum_channels_f32(const float* y, float* out, int64_t S, int32_t C, int64_t T, int64_t ys, int64_t os,
+                             void* cuda_stream) {
+  if (S < 0 || T < 0 || C <= 0) return fail(ALZ_ERR_INVALID, "bad size");
+  if (S == 0 || T == 0) return ALZ_OK;
+  if (!y || !out) return fail(ALZ_ERR_INVALID, "null buffer");
+  const long long n = (long long)S * T;
+  alz_sum_channels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(y, out, S, C, T, ys, os);
+  ALZ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ALZ_OK;
+}
+
+}  // extern "C"
