@@ -25,7 +25,7 @@ KIND_GENERIC = 2
 
 #: every symbol include/alz_b200.h declares (tests check the library exports them all)
 SYMBOLS = (
-  "alz_last_error", "alz_abi_version", "alz_device_count", "alz_plan_create", "alz_plan_destroy",
+  "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_destroy",
   "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
   "alz_apply_f32_host", "alz_sum_channels_f32", "alz_launch_count",
 )
@@ -63,6 +63,8 @@ def lib():
   L.alz_last_error.argtypes = []
   L.alz_abi_version.restype = i32
   L.alz_device_count.restype = i32
+  L.alz_set_device.restype = i32
+  L.alz_set_device.argtypes = [i32]
   L.alz_plan_create.restype = i32
   L.alz_plan_create.argtypes = [vp, vp, i32, i32, ctypes.POINTER(vp)]
   L.alz_plan_destroy.restype = None
@@ -181,6 +183,10 @@ def sum_channels(y_ptr, out_ptr, n_streams, n_channels, n_samples, y_stride, out
 
 def device_count():
   return lib().alz_device_count()
+
+
+def set_device(index):
+  _check(lib().alz_set_device(int(index)))
 
 
 def launch_count():

@@ -1,0 +1,189 @@
+"""Device engine: compiled plans, device buffers and the lazy block pump.
+
+Everything numeric happens in the native library (``_capi``); PyTorch is used only as
+the container of device memory, CUDA streams and (in :mod:`audiolazy_b200.parallel`)
+``torch.distributed``. No filtering arithmetic is done in Python or numpy here.
+"""
+from __future__ import annotations
+
+import itertools as it
+import threading
+from collections import deque
+
+import numpy as np
+
+from . import _capi
+from .stream import Stream
+
+#: block sizes of the lazy pump: start small (low latency for ``take(few)``), grow
+#: geometrically, cap at MAX_BLOCK samples per launch.
+FIRST_BLOCK = 256
+MAX_BLOCK = 1 << 20
+
+_lock = threading.Lock()
+_cache = {}
+
+
+def torch_mod():
+  import torch
+  if not torch.cuda.is_available():
+    raise _capi.NativeError("audiolazy_b200 needs a CUDA device (there is no CPU evaluator)")
+  return torch
+
+
+def _key(bank_sections):
+  return tuple(tuple((tuple(b), tuple(a)) for b, a in channel) for channel in bank_sections)
+
+
+class DeviceBank(object):
+  """A plan (bank of cascades) bound to the current CUDA device plus the torch-side
+  helpers to allocate state / output and launch on torch's current stream."""
+
+  def __init__(self, bank_sections):
+    torch = torch_mod()
+    self.device = torch.device("cuda", torch.cuda.current_device())
+    _capi.set_device(self.device.index)
+    self.plan = _capi.Plan(bank_sections)
+    self.n_channels = self.plan.n_channels
+    self._sections = bank_sections
+
+  # ---- state -------------------------------------------------------------------------
+  def _pad_init(self, init, depth):
+    if init is None:
+      return None
+    C, K = self.plan.n_channels, self.plan.n_sections
+    arr = np.zeros((C, K, max(depth, 1)), dtype=np.float64)
+    for c, channel in enumerate(init):
+      for k, hist in enumerate(channel):
+        if len(hist) > depth:
+          raise ValueError("initial history longer than the section's delay line")
+        arr[c, k, :len(hist)] = hist
+    return arr[:, :, :depth] if depth else None
+
+  def new_state(self, n_streams, xinit=None, yinit=None):
+    """Device state (torch float64) for ``n_streams`` streams; ``xinit`` / ``yinit`` are
+    per channel, per section lists of initial delays (``zero`` / ``memory``)."""
+    torch = torch_mod()
+    n = max(1, self.plan.state_doubles(n_streams))
+    state = torch.empty(n, dtype=torch.float64, device=self.device)
+    xi = self._pad_init(xinit, self.plan.xd)
+    yi = self._pad_init(yinit, self.plan.yd)
+    if xi is not None and not xi.any():
+      xi = None
+    if yi is not None and not yi.any():
+      yi = None
+    self.plan.state_init(state.data_ptr(), n_streams, xi, yi, torch.cuda.current_stream(self.device).cuda_stream)
+    return state
+
+  # ---- launches ----------------------------------------------------------------------
+  def apply(self, x, state, out=None):
+    """``x``: CUDA float32 tensor ``[S, T]`` (rows may be strided); returns ``[S, C, T]``."""
+    torch = torch_mod()
+    if x.dim() == 1:
+      x = x.unsqueeze(0)
+    if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 2:
+      raise ValueError("x must be a CUDA float32 tensor of shape [streams, samples]")
+    if x.stride(1) != 1:
+      x = x.contiguous()
+    S, T = x.shape
+    if out is None:
+      out = torch.empty((S, self.n_channels, T), dtype=torch.float32, device=x.device)
+    elif out.shape != (S, self.n_channels, T) or out.dtype != torch.float32 or not out.is_contiguous():
+      raise ValueError("out must be a contiguous float32 tensor [S, C, T]")
+    self.plan.apply(x.data_ptr(), out.data_ptr(), state.data_ptr(), S, T, x.stride(0) if S > 1 else max(T, 1),
+                    T, torch.cuda.current_stream(x.device).cuda_stream)
+    return out
+
+  def sum_channels(self, y):
+    torch = torch_mod()
+    S, C, T = y.shape
+    out = torch.empty((S, T), dtype=torch.float32, device=y.device)
+    _capi.sum_channels(y.data_ptr(), out.data_ptr(), S, C, T, T, T, torch.cuda.current_stream(y.device).cuda_stream)
+    return out
+
+
+def device_bank(bank_sections):
+  """Cached :class:`DeviceBank` for a bank given as channels -> sections -> (b, a)."""
+  torch = torch_mod()
+  key = (torch.cuda.current_device(), _key(bank_sections))
+  with _lock:
+    db = _cache.get(key)
+    if db is None:
+      if len(_cache) > 256:
+        _cache.clear()
+      db = _cache[key] = DeviceBank(bank_sections)
+  return db
+
+
+def _blocks(seq):
+  """Yield float32 numpy blocks of the input iterable (whole thing at once when it is a
+  sized container, geometrically growing read-ahead otherwise)."""
+  if isinstance(seq, np.ndarray) and seq.ndim == 1:
+    for i in range(0, len(seq), MAX_BLOCK):
+      yield np.ascontiguousarray(seq[i:i + MAX_BLOCK], dtype=np.float32)
+    return
+  if isinstance(seq, (list, tuple)):
+    for i in range(0, len(seq), MAX_BLOCK):
+      yield np.asarray(seq[i:i + MAX_BLOCK], dtype=np.float32)
+    return
+  src = iter(seq)
+  n = FIRST_BLOCK
+  while True:
+    chunk = list(it.islice(src, n))
+    if not chunk:
+      return
+    yield np.asarray(chunk, dtype=np.float32)
+    if len(chunk) < n:
+      return
+    n = min(n * 4, MAX_BLOCK)
+
+
+def _pump(db, seq, xinit, yinit, sum_channels):
+  """Generator of per-block results: numpy float32 ``[C, n]`` (or ``[n]`` when summed)."""
+  torch = torch_mod()
+  state = None
+  for xb in _blocks(seq):
+    if state is None:
+      state = db.new_state(1, xinit, yinit)
+    x_dev = torch.from_numpy(xb).to(db.device, non_blocking=False)
+    y_dev = db.apply(x_dev, state)
+    if sum_channels:
+      yield db.sum_channels(y_dev)[0].cpu().numpy()
+    else:
+      yield y_dev[0].cpu().numpy()
+
+
+def filter_stream(bank_sections, seq, xinit, yinit, sum_channels=False):
+  """Lazy Stream of a single-output filter call (one channel, or the channel sum)."""
+  db = device_bank(bank_sections)   # errors (zero gain, no device) raise at call time, like the reference
+
+  def gen():
+    for block in _pump(db, seq, xinit, yinit, sum_channels):
+      row = block if sum_channels else block[0]
+      for value in row.tolist():
+        yield value
+
+  return Stream(gen())
+
+
+def bank_streams(bank_sections, seq, xinit, yinit):
+  """One lazy Stream per channel, fed by a shared pump (like a tee: a channel consumed
+  far ahead of the others buffers their samples)."""
+  db = device_bank(bank_sections)
+  C = db.n_channels
+  queues = [deque() for _ in range(C)]
+  pump = _pump(db, seq, xinit, yinit, False)
+
+  def channel(c):
+    while True:
+      while not queues[c]:
+        try:
+          block = next(pump)
+        except StopIteration:
+          return
+        for q, row in zip(queues, block):
+          q.append(row.tolist())
+      for value in queues[c].popleft():
+        yield value
+
+  return [Stream(channel(c)) for c in range(C)]

@@ -1,0 +1,99 @@
+"""Filterbank object: one input fanned out to many filters.
+
+The reference has no bank class -- its only bank usage is a Python loop over centre
+frequencies applying each cascade to a copy of the input
+(``examples/gammatone_plots.py:42-73``; fan-out through ``thub``, reference
+``audiolazy/lazy_stream.py:573-630``). :class:`FilterBank` is that loop as an object,
+with each channel exactly the reference's filter, evaluated for all channels (and any
+number of independent input streams) by ONE kernel launch per block.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _engine
+from .filters import CascadeFilter, FilterList, LinearFilter, _seed_histories
+
+__all__ = ["FilterBank", "BankState"]
+
+
+class BankState(object):
+  """Device state of a bank for ``n_streams`` input streams: carries every recurrence
+  from one :meth:`FilterBank.apply` call to the next (endless inputs in blocks)."""
+
+  def __init__(self, bank, n_streams, memory=None, zero=0.):
+    self.bank = bank
+    self.n_streams = int(n_streams)
+    seeds = [_seed_histories(ch, memory, zero) for ch in bank.sections()]
+    self.tensor = bank.device_bank().new_state(self.n_streams, [s[0] for s in seeds], [s[1] for s in seeds])
+
+
+class FilterBank(list):
+  """List of LTI filters (``ZFilter`` / all-LTI ``CascadeFilter``) sharing one input.
+
+  * ``bank(seq)`` -> list of Streams, one per channel (``[f(seq_copy) for f in bank]``).
+  * ``bank.apply(x)`` -> CUDA tensor ``y[S, C, T]`` for a CUDA float32 tensor ``x[S, T]``
+    of ``S`` independent streams; pass ``state=bank.new_state(S)`` to continue streams
+    across calls.
+  * ``bank.apply_host(x)`` -> the same through numpy host buffers (copies inside).
+  """
+
+  def __init__(self, filters=()):
+    list.__init__(self, filters)
+    self._sections = None
+    self.freqs = None
+    self.rate = None
+
+  def sections(self):
+    """Channels -> sections -> ``(b, a)``: the table handed to ``alz_plan_create``."""
+    if self._sections is None or len(self._sections) != len(self):
+      table = []
+      for f in self:
+        if isinstance(f, CascadeFilter):
+          secs = f._flat_sections()
+          if secs is None:
+            raise NotImplementedError("bank channels must be LTI filters")
+        elif isinstance(f, LinearFilter):
+          secs = f.sections()
+        elif not callable(f):
+          secs = LinearFilter(f).sections()
+        else:
+          raise NotImplementedError("bank channels must be LTI filters")
+        table.append(secs)
+      self._sections = table
+    return self._sections
+
+  def device_bank(self):
+    return _engine.device_bank(self.sections())
+
+  def new_state(self, n_streams, memory=None, zero=0.):
+    return BankState(self, n_streams, memory=memory, zero=zero)
+
+  # -- lazy API ------------------------------------------------------------------------
+  def __call__(self, seq, memory=None, zero=0.):
+    secs = self.sections()
+    seeds = [_seed_histories(ch, memory, zero) for ch in secs]
+    return _engine.bank_streams(secs, seq, [s[0] for s in seeds], [s[1] for s in seeds])
+
+  # -- batch API -----------------------------------------------------------------------
+  def apply(self, x, state=None, out=None):
+    db = self.device_bank()
+    if x.dim() == 1:
+      x = x.unsqueeze(0)
+    if state is None:
+      state = self.new_state(x.shape[0])
+    if state.n_streams != x.shape[0]:
+      raise ValueError("state was created for %d streams, x has %d" % (state.n_streams, x.shape[0]))
+    return db.apply(x, state.tensor, out=out)
+
+  def apply_host(self, x, out=None, state=None):
+    """``x``: float32 ndarray ``[S, T]`` (or ``[T]``) on the host; returns ndarray ``[S, C, T]``.
+    Goes through ``alz_apply_f32_host`` (pipelined H2D / kernel / D2H)."""
+    db = self.device_bank()
+    x = np.asarray(x, dtype=np.float32)
+    state_ptr = None
+    if state is not None:
+      if state.n_streams != (1 if x.ndim == 1 else x.shape[0]):
+        raise ValueError("state / input stream count mismatch")
+      state_ptr = state.tensor.data_ptr()
+    return db.plan.apply_host(x, out, state_ptr)

@@ -174,6 +174,11 @@ int32_t alz_device_count(void) {
   return n;
 }
 
+int32_t alz_set_device(int32_t device) {
+  ALZ_CUDA(cudaSetDevice(device));
+  return ALZ_OK;
+}
+
 int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int32_t KM, alz_plan** out) {
   if (!out) return fail(ALZ_ERR_INVALID, "out is null");
   *out = nullptr;
@@ -481,7 +486,12 @@ int32_t alz_apply_f32(const alz_plan* p, const float* x, float* y, double* state
   if (S == 0 || T == 0) return ALZ_OK;
   if (!x || !y || !state) return fail(ALZ_ERR_INVALID, "null buffer");
   if (xs < T || ys < T) return fail(ALZ_ERR_INVALID, "row stride shorter than n_samples");
-  return apply_impl(p, x, y, state, (long long)S * p->C, S, T, xs, ys, (cudaStream_t)cuda_stream);
+  int cur = -1;
+  ALZ_CUDA(cudaGetDevice(&cur));
+  if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
+  const int rc = apply_impl(p, x, y, state, (long long)S * p->C, S, T, xs, ys, (cudaStream_t)cuda_stream);
+  if (cur != p->device) cudaSetDevice(cur);
+  return rc;
 }
 
 int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, double* state, int64_t S, int64_t T,

@@ -83,6 +83,10 @@ int32_t alz_abi_version(void);
 /* Number of usable CUDA devices (0 if none; never fails). */
 int32_t alz_device_count(void);
 
+/* Make `device` the current CUDA device of the calling thread for this library
+ * (plans are created on the current device; apply calls use the plan's device). */
+int32_t alz_set_device(int32_t device);
+
 /*
  * Build a plan for a bank of `n_channels` cascades of up to `max_sections`
  * direct-form-I sections on the CURRENT CUDA device.

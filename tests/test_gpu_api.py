@@ -1,0 +1,164 @@
+"""The reference-facing Python API on a GPU: filters are callables that take an iterable and
+return a Stream (reference lazy_filters.py:975-978); known answers are the reference's own
+doctests / tests and the golden vectors."""
+import itertools as it
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err, signal
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ab():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  torch.cuda.set_device(0)
+  import audiolazy_b200
+  return audiolazy_b200
+
+
+def test_reference_doctests(ab):
+  z, ZFilter, Stream = ab.z, ab.ZFilter, ab.Stream
+  filt = (1 + z ** -1) / (1 - z ** -1)                        # lazy_filters.py:722-726
+  res = filt([1, 5, -4, -7, 9])
+  assert isinstance(res, Stream)
+  assert list(res) == [1.0, 7.0, 8.0, -3.0, -1.0]
+  filt = ZFilter([1, 1], [1, -1])                             # :731-742
+  result = list(filt([1, 5, -4, -7, 9], memory=[3], zero=0))
+  assert result == [4, 10, 11, 0, 2]
+  assert list((filt * z ** -1)(result, zero=0)) == [0, 4, 18, 39, 50]
+  assert list((1 + z ** -1)([1.0, 2.0, 3.0])) == [1.0, 3.0, 5.0]      # :877-882
+  casc = ab.CascadeFilter(z ** -1, 2 * (1 - z ** -3))                   # :982-985
+  data = Stream(1, 3, 5, 3, 1, -1, -3, -5, -3, -1)                      # endless
+  assert casc(data, zero=0).take(15) == [0, 2, 6, 10, 4, -4, -12, -12, -12, -4, 4, 12, 12, 12, 4]
+  filt = 1 + z ** -1 - z ** -2                                          # :1040-1045
+  pfilt = ab.ParallelFilter(1 + z ** -1, -z ** -2)
+  assert list(filt(range(100))) == list(pfilt(range(100)))
+  assert list(filt(range(10), zero=0)) == [0, 1, 3, 4, 5, 6, 7, 8, 9, 10]
+  acc = 1 / (1 - z ** -1)                                               # __init__.py:27-30 (accumulator)
+  assert acc(Stream(it.count())).take(6) == [0.0, 1.0, 3.0, 6.0, 10.0, 15.0]
+
+
+def test_lfilter_grid(ab):
+  """reference tests/test_filters_extdep.py:41-47 (ZFilter vs scipy.signal.lfilter)."""
+  from scipy.signal import lfilter
+  for a in [[1.], [3.], [1., 3.], [15., -17.2], [-18., 9.8, 0., 14.3]]:
+    for b in [[1.], [-1.], [1., 0., -1.], [1., 3.]]:
+      for data in [list(range(5)), list(range(5, 0, -1)), [7, 22, -5], [8., 3., 15.]]:
+        got = list(ab.ZFilter(b, a)(data))
+        want = lfilter(b, a, data).tolist()
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-30), (a, b, data, got, want)
+
+
+def test_identity_gain_delay_empty_lists(ab):
+  z, Stream = ab.z, ab.Stream                                    # reference tests/test_filters.py:47-114, :557-566
+  data = [1.5, -2.0, 0.25, 8.0]
+  assert list(ab.ZFilter(1)(data)) == data
+  assert list((0.5 * z ** 0)(data)) == [v * 0.5 for v in data]
+  assert list((z ** -2)(data)) == [0.0, 0.0, 1.5, -2.0]
+  assert list((z ** -2)(data, zero=7.0)) == [7.0, 7.0, 1.5, -2.0]
+  assert list(ab.CascadeFilter()(data)) == data
+  assert list(ab.ParallelFilter()(data)) == [0.0] * 4
+  assert list(ab.ParallelFilter()(data, zero=2.5)) == [2.5] * 4
+  assert list(ab.ZFilter([1, 1])(Stream(data))) == [1.5, -0.5, -1.75, 8.25]
+  one_pole = 1 / (1 - 0.5 * z ** -1)
+  want, m = [], 0.0
+  for v in data:
+    m = v + 0.5 * m
+    want.append(m)
+  assert list(one_pole(data)) == want
+  assert list(ab.CascadeFilter(2.0, z ** -1)(data)) == [0.0, 3.0, -4.0, 0.5]     # bare numbers are gains
+  mixed = ab.CascadeFilter(z ** -1, lambda s: Stream(s) * 2)                      # non-linear member: generic path
+  assert list(mixed(data)) == [0.0, 3.0, -4.0, 0.5]
+  with pytest.raises(ValueError, match="Non-causal"):
+    (z + 1)(data)
+  with pytest.raises(NotImplementedError):
+    (1 + Stream(1, 2) * z ** -1)(data)
+
+
+def test_configs_through_the_python_api(ab, designs, vectors):
+  y = np.array(list(ab.ZFilter([1, 7, 2], [1, 0.5, 0.2])(signal(1, 48000).tolist())))      # cfg 1
+  assert rel_err(y, vectors["cfg1_y"]) <= TOL
+  casc = ab.CascadeFilter([ab.ZFilter(r[:3], r[3:]) for r in designs["cfg2_sos"]])          # cfg 2
+  y = np.array(list(casc(ab.Stream(signal(2, 50000).tolist()))))
+  assert rel_err(y, vectors["cfg2_y"]) <= TOL
+  f = ab.ZFilter([0.5, -0.25, 2.0], [2.0, 0.5, -0.3])
+  xs = signal(3, 64).tolist()
+  assert rel_err(list(f(xs, memory=[0.75, -1.5], zero=0.125)), vectors["seed_single_y"]) <= TOL
+  assert rel_err(list(f(xs, memory=[0.75], zero=-0.5)), vectors["seed_short_memory_y"]) <= TOL
+  assert rel_err(list(f(xs, memory=lambda n: [0.75, -1.5, 9.0][:n], zero=0.125)), vectors["seed_single_y"]) <= TOL
+  casc3 = ab.CascadeFilter(ab.ZFilter([1, 0.5], [1, -0.9]), ab.ZFilter([0.3, 0.2, 0.1], [1, 0.4, 0.2]),
+                           ab.ZFilter([2.0], [1, 0, 0.81]))
+  assert rel_err(list(casc3(xs, memory=[0.3, -0.2], zero=0.25)), vectors["seed_cascade_y"]) <= TOL
+  par = ab.ParallelFilter(ab.ZFilter([1, 1], [1, -0.5]), ab.ZFilter([0.5], [1, 0.3, 0.1]), ab.ZFilter([0, 0, 2.0]))
+  assert rel_err(list(par(xs)), vectors["parallel_y"]) <= TOL
+  xg = signal(4, 4000).tolist()
+  assert rel_err(list(ab.comb.fb(37, 0.8)(xg)), vectors["comb_fb_y"]) <= TOL
+  assert rel_err(list(ab.comb.ff(100, -0.5)(xg)), vectors["comb_ff_y"]) <= TOL
+
+
+@pytest.mark.parametrize("strategy", ["slaney", "klapuri", "sampled"])
+def test_gammatone_channels_and_bank(ab, vectors, strategy):
+  s, Hz = ab.sHz(48000)
+  x = signal(0, 8000)
+  bank = ab.gammatone_bank(strategy=strategy)
+  chans = vectors["bank_channels"]
+  c = int(chans[3])
+  bw = ab.gammatone_erb_constants(4)[0] * ab.erb(bank.freqs[c] * Hz, Hz)       # examples/gammatone_plots.py:47,64
+  single = ab.gammatone[strategy](bank.freqs[c] * Hz, bw)
+  assert rel_err(list(single(x.tolist())), vectors["bank_%s_y" % strategy][3]) <= TOL
+  streams = bank(x.tolist())                                                   # one input fanned out to 64 Streams
+  assert len(streams) == 64 and all(isinstance(st, ab.Stream) for st in streams)
+  got = np.array([list(streams[int(i)]) for i in chans])
+  assert rel_err(got, vectors["bank_%s_y" % strategy]) <= TOL
+  y = bank.apply_host(np.stack([x, signal(7, 8000)]))                          # batch API, host buffers
+  assert y.shape == (2, 64, 8000)
+  assert rel_err(y[0][chans], vectors["bank_%s_y" % strategy]) <= TOL
+
+
+def test_lazy_pump_and_batch_state(ab):
+  import torch
+  z = ab.z
+  filt = 1 / (1 - 0.999 * z ** -1)
+  pulled = []
+
+  def source():
+    for i in it.count():
+      pulled.append(i)
+      yield 1.0
+
+  out = filt(source())
+  first = out.take(10)
+  assert len(first) == 10 and len(pulled) <= 2048           # read-ahead is bounded, the input is endless
+  more = out.take(5000)
+  want, m = [], 0.0
+  for _ in range(5010):
+    m = 1.0 + 0.999 * m
+    want.append(m)
+  assert rel_err(first + more, want) <= TOL
+  bank = ab.gammatone_bank(freqs=ab.erb_space(n=8), strategy="slaney")
+  x = torch.from_numpy(np.stack([signal(40 + i, 4096) for i in range(70)])).cuda()
+  whole = bank.apply(x)
+  state = bank.new_state(70)
+  parts = [bank.apply(x[:, a:b].contiguous(), state=state) for a, b in [(0, 1000), (1000, 1001), (1001, 4096)]]
+  assert torch.equal(torch.cat(parts, dim=2), whole)
+  assert rel_err(whole.cpu().numpy(), oracle.bank_apply(x.cpu().numpy(), bank.sections())) <= TOL
+
+
+def test_two_gpu_channel_sharding(ab):
+  import torch
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs 2 GPUs")
+  # one process, two devices: the same plan machinery on another device index
+  bank = ab.gammatone_bank(freqs=ab.erb_space(n=8), strategy="slaney")
+  x = np.stack([signal(60 + i, 2048) for i in range(33)])
+  with torch.cuda.device(1):
+    y1 = bank.apply(torch.from_numpy(x).cuda()).cpu().numpy()
+  y0 = bank.apply(torch.from_numpy(x).cuda()).cpu().numpy()
+  assert np.array_equal(y0, y1)

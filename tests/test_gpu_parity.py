@@ -1,0 +1,213 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the golden vectors
+the reference produced. Tolerance: the north star's <= 1e-5 relative (to each output row's
+peak) for float32 I/O; measured errors are ~6e-8 (float32 rounding of the float64 result)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import rel_err, signal
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def gpu():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  torch.cuda.set_device(0)
+  from audiolazy_b200 import _capi
+  assert _capi.device_count() >= 1
+
+  class G:
+    pass
+
+  g = G()
+  g.torch = torch
+  g.capi = _capi
+  g.dev = torch.device("cuda:0")
+
+  def run(plan, x, xinit=None, yinit=None, splits=None):
+    x = np.atleast_2d(np.asarray(x, dtype=np.float32))
+    S, T = x.shape
+    C = plan.n_channels
+    xd = torch.from_numpy(x).to(g.dev)
+    y = torch.full((S, C, max(T, 1)), float("nan"), dtype=torch.float32, device=g.dev)[:, :, :T].contiguous()
+    st = torch.empty(max(1, plan.state_doubles(S)), dtype=torch.float64, device=g.dev)
+    cur = torch.cuda.current_stream().cuda_stream
+    plan.state_init(st.data_ptr(), S, xinit, yinit, cur)
+    t0 = 0
+    for n in (splits or [T]):
+      plan.apply(xd.data_ptr() + 4 * t0, y.data_ptr() + 4 * t0, st.data_ptr(), S, n, max(T, 1), max(T, 1), cur)
+      t0 += n
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+  g.run = run
+  return g
+
+
+@pytest.mark.parametrize("name", ["slaney", "klapuri", "sampled"])
+def test_bank_vs_golden_and_oracle(gpu, designs, vectors, name):
+  bank = designs["bank_" + name]
+  plan = gpu.capi.Plan(bank)
+  assert plan.kind == (gpu.capi.KIND_GENERIC if name == "sampled" else gpu.capi.KIND_BIQUAD)
+  x = np.stack([signal(0, 8000), signal(7, 8000), signal(8, 8000)])
+  y = gpu.run(plan, x)
+  assert rel_err(y[0][vectors["bank_channels"]], vectors["bank_%s_y" % name]) <= TOL      # the reference's own output
+  assert rel_err(y, oracle.bank_apply(x, bank)) <= TOL                                    # all 64 channels, 3 streams
+  imp = np.zeros(2000, dtype=np.float32)
+  imp[0] = 1
+  yi = gpu.run(plan, imp)
+  assert rel_err(yi[0][[4, 40]], vectors["bank_%s_impulse" % name]) <= TOL
+
+
+def test_cfg1_cfg2(gpu, designs, vectors):
+  plan = gpu.capi.Plan([[([1, 7, 2], [1, 0.5, 0.2])]])
+  assert rel_err(gpu.run(plan, signal(1, 48000))[0, 0], vectors["cfg1_y"]) <= TOL
+  bank2 = [[(r[:3], r[3:]) for r in designs["cfg2_sos"]]]
+  plan = gpu.capi.Plan(bank2)
+  assert plan.monic and plan.n_sections == 4
+  assert rel_err(gpu.run(plan, signal(2, 50000))[0, 0], vectors["cfg2_y"]) <= TOL
+  x = signal(2, 1000000)                         # BASELINE cfg 2 at full size, against the oracle
+  assert rel_err(gpu.run(plan, x)[0, 0], oracle.bank_apply(x, bank2)[0, 0]) <= TOL
+
+
+def test_memory_zero_seeding(gpu, designs, vectors):
+  xs = signal(3, 64)
+  f = ([0.5, -0.25, 2.0], [2.0, 0.5, -0.3])
+  plan = gpu.capi.Plan([[f]])
+  y = gpu.run(plan, xs, xinit=[[[0.125, 0.125]]], yinit=[[[0.75, -1.5]]])
+  assert rel_err(y[0, 0], vectors["seed_single_y"]) <= TOL
+  y = gpu.run(plan, xs, xinit=[[[-0.5, -0.5]]], yinit=[[[-0.5, 0.75]]])
+  assert rel_err(y[0, 0], vectors["seed_short_memory_y"]) <= TOL
+  casc = designs["seed_cascade"]
+  plan = gpu.capi.Plan([casc])
+  K = plan.n_sections
+  xi = np.zeros((1, K, 2))
+  yi = np.zeros((1, K, 2))
+  for k, (b, a) in enumerate(casc):
+    xi[0, k, :len(b) - 1] = 0.25
+    mem = [0.3, -0.2][:len(a) - 1]
+    yi[0, k, :len(a) - 1] = [0.25] * (len(a) - 1 - len(mem)) + mem
+  y = gpu.run(plan, xs, xinit=xi, yinit=yi)
+  assert rel_err(y[0, 0], vectors["seed_cascade_y"]) <= TOL
+  for splits in ([1, 63], [1, 1, 62], [2, 62], [33, 31]):
+    assert np.array_equal(gpu.run(plan, xs, xinit=xi, yinit=yi, splits=splits), y)
+
+
+def test_gain_divisor_and_generic_kernel(gpu, designs, vectors):
+  xs = signal(3, 64)
+  y = gpu.run(gpu.capi.Plan([[([1.0, 3.0], [-18.0, 9.8, 0.0, 14.3])]]), xs)
+  assert rel_err(y[0, 0], vectors["a0_not_one_y"]) <= TOL
+  y = gpu.run(gpu.capi.Plan([[([1.0, 0.0, -1.0], [-1.0, 0.5])]]), xs)
+  assert rel_err(y[0, 0], vectors["a0_minus_one_y"]) <= TOL
+  xg = signal(4, 4000)
+  for bank, key in [([[(designs["generic_b"], designs["generic_a"])]], "generic_y"),
+                    ([designs["comb_fb_37_0.8"]], "comb_fb_y"), ([designs["comb_ff_100_-0.5"]], "comb_ff_y")]:
+    plan = gpu.capi.Plan(bank)
+    assert plan.kind == gpu.capi.KIND_GENERIC
+    y = gpu.run(plan, xg)
+    assert rel_err(y[0, 0], vectors[key]) <= TOL
+    assert np.array_equal(gpu.run(plan, xg, splits=[1, 5, 100, 3894]), y)     # ring buffers are block-exact
+
+
+@pytest.mark.parametrize("C,S,T", [(1, 1, 1), (1, 1, 2), (1, 3, 3), (1, 100, 1000), (3, 37, 257), (5, 64, 31), (5, 33, 32),
+                                   (48, 3, 33), (64, 5, 999), (64, 32, 64), (7, 65, 100)])
+def test_ragged_shapes(gpu, designs, C, S, T):
+  bank = designs["bank_slaney"][:C]
+  plan = gpu.capi.Plan(bank)
+  x = np.stack([signal(100 + i, T) for i in range(S)])
+  assert rel_err(gpu.run(plan, x), oracle.bank_apply(x, bank)) <= TOL
+
+
+def test_block_split_is_bit_exact(gpu, designs):
+  x = np.stack([signal(0, 8000), signal(7, 8000)])
+  for name in ("slaney", "klapuri"):
+    plan = gpu.capi.Plan(designs["bank_" + name])
+    y = gpu.run(plan, x)
+    assert np.array_equal(gpu.run(plan, x, splits=[1, 1, 30, 33, 935, 7000]), y)
+    assert np.array_equal(gpu.run(plan, x, splits=[4000, 4000]), y)
+
+
+def test_unaligned_pointers_and_strides(gpu, designs):
+  torch = gpu.torch
+  bank = designs["bank_slaney"]
+  plan = gpu.capi.Plan(bank)
+  S, T = 3, 1001
+  xx = np.stack([signal(200 + i, T) for i in range(S)])
+  xd = torch.zeros(S * 1003 + 1, dtype=torch.float32, device=gpu.dev)
+  yd = torch.zeros(S * 64 * 1005 + 1, dtype=torch.float32, device=gpu.dev)
+  xd[1:].view(S, 1003)[:, :T] = torch.from_numpy(xx).to(gpu.dev)
+  st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=gpu.dev)
+  plan.apply(xd.data_ptr() + 4, yd.data_ptr() + 4, st.data_ptr(), S, T, 1003, 1005, torch.cuda.current_stream().cuda_stream)
+  torch.cuda.synchronize()
+  y = yd[1:].view(S * 64, 1005)[:, :T].cpu().numpy().reshape(S, 64, T)
+  assert rel_err(y, oracle.bank_apply(xx, bank)) <= TOL
+  assert np.array_equal(y, gpu.run(plan, xx))          # scalar and vector paths agree bit for bit
+
+
+def test_host_path_and_state_carry(gpu, designs):
+  torch = gpu.torch
+  bank = designs["bank_klapuri"][:16]
+  plan = gpu.capi.Plan(bank)
+  x = np.stack([signal(300 + i, 5000) for i in range(9)])
+  want = gpu.run(plan, x)
+  assert np.array_equal(plan.apply_host(x), want)
+  st = torch.zeros(plan.state_doubles(9), dtype=torch.float64, device=gpu.dev)
+  a = plan.apply_host(np.ascontiguousarray(x[:, :1234]), state_ptr=st.data_ptr())
+  b = plan.apply_host(np.ascontiguousarray(x[:, 1234:]), state_ptr=st.data_ptr())
+  assert np.array_equal(np.concatenate([a, b], axis=2), want)
+
+
+def test_parallel_channel_sum(gpu, designs, vectors):
+  torch = gpu.torch
+  plan = gpu.capi.Plan(designs["parallel"])
+  xs = signal(3, 64)
+  y = torch.from_numpy(gpu.run(plan, xs)).to(gpu.dev)
+  out = torch.empty((1, 64), dtype=torch.float32, device=gpu.dev)
+  gpu.capi.sum_channels(y.data_ptr(), out.data_ptr(), 1, 3, 64, 64, 64, torch.cuda.current_stream().cuda_stream)
+  torch.cuda.synchronize()
+  assert rel_err(out.cpu().numpy()[0], vectors["parallel_y"]) <= TOL
+
+
+def test_error_codes(gpu):
+  with pytest.raises(ZeroDivisionError):
+    gpu.capi.Plan([[([1.0], [0.0, 1.0])]])
+  with pytest.raises(ValueError):
+    gpu.capi.Plan([[([float("nan")], [1.0])]])
+  plan = gpu.capi.Plan([[([1.0], [1.0])], []])        # second channel: empty cascade = identity
+  x = signal(5, 100)
+  y = gpu.run(plan, x)
+  assert np.array_equal(y[0, 0], x) and np.array_equal(y[0, 1], x)
+
+
+def test_full_size_properties(gpu, designs):
+  """BASELINE cfg 4 (64 ch x 4096 streams x 16384 samples), where the oracle cannot go:
+  stream independence, block-split exactness and spot rows against the oracle."""
+  torch = gpu.torch
+  bank = designs["bank_slaney"]
+  plan = gpu.capi.Plan(bank)
+  S, T, C = 4096, 16384, 64
+  g = torch.Generator(device=gpu.dev)
+  g.manual_seed(0)
+  x = torch.rand((S, T), device=gpu.dev, generator=g) * 2 - 1
+  x[S // 2:] = x[:S // 2]                     # second half duplicates the first
+  cur = torch.cuda.current_stream().cuda_stream
+  y = torch.empty((S, C, T), dtype=torch.float32, device=gpu.dev)
+  st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=gpu.dev)
+  plan.apply(x.data_ptr(), y.data_ptr(), st.data_ptr(), S, T, T, T, cur)
+  torch.cuda.synchronize()
+  assert torch.equal(y[:S // 2], y[S // 2:])   # same input, same output, whatever the lane / warp / SM
+  rows = [0, 1, 31, 32, 2047, 777]
+  want = oracle.bank_apply(x[rows].cpu().numpy(), bank)
+  assert rel_err(y[rows].cpu().numpy(), want) <= TOL
+  y2 = torch.empty_like(y)
+  st.zero_()
+  half = T // 2 + 32 * 3 + 5
+  plan.apply(x.data_ptr(), y2.data_ptr(), st.data_ptr(), S, half, T, T, cur)
+  plan.apply(x.data_ptr() + 4 * half, y2.data_ptr() + 4 * half, st.data_ptr(), S, T - half, T, T, cur)
+  torch.cuda.synchronize()
+  assert torch.equal(y, y2)
+  assert bool(torch.isfinite(y[::97]).all())
