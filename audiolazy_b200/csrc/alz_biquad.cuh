@@ -125,23 +125,29 @@ struct AlzBiquadCore {
     return (float)(MONIC ? G * in : in);
   }
 
-  // Filter my row of the tile in place: float32 in, float32 out.
-  __device__ __forceinline__ void tile(float* row, int nvalid, long long n_done) {
+  // Filter my row of the tile in place: float32 in, float32 out.  `swz` is the XOR
+  // applied to the 16-byte chunk index (0 for the padded cp.async tile, lane & 7 for the
+  // TMA 128-byte-swizzled tile).
+  __device__ __forceinline__ void tile(float* row, int swz, int nvalid, long long n_done) {
     if (nvalid == ALZ_TT && n_done >= 2) {
+      float4 xf = *reinterpret_cast<const float4*>(row + ((0 ^ swz) << 2));
 #pragma unroll kAlzGroupUnroll
       for (int g = 0; g < ALZ_TT / 4; ++g) {
-        const float4 xf = *reinterpret_cast<const float4*>(row + 4 * g);
+        float* p = row + ((g ^ swz) << 2);
+        const float4 xc = xf;
+        if (g + 1 < ALZ_TT / 4) xf = *reinterpret_cast<const float4*>(row + (((g + 1) ^ swz) << 2));   // prefetch
         float4 o;
-        o.x = step_alias((double)xf.x);
-        o.y = step_alias((double)xf.y);
-        o.z = step_alias((double)xf.z);
-        o.w = step_alias((double)xf.w);
-        *reinterpret_cast<float4*>(row + 4 * g) = o;
+        o.x = step_alias((double)xc.x);
+        o.y = step_alias((double)xc.y);
+        o.z = step_alias((double)xc.z);
+        o.w = step_alias((double)xc.w);
+        *reinterpret_cast<float4*>(p) = o;
       }
     } else {
       for (int j = 0; j < nvalid; ++j) {
-        const double xin = (double)row[j];
-        row[j] = (n_done + j < 2) ? step_explicit(xin) : step_alias(xin);
+        float* p = row + ((((j >> 2) ^ swz) << 2) | (j & 3));
+        const double xin = (double)*p;
+        *p = (n_done + j < 2) ? step_explicit(xin) : step_alias(xin);
       }
     }
   }

@@ -3,6 +3,7 @@
 #include "../../include/alz_b200.h"
 #include "alz_biquad.cuh"
 #include "alz_generic.cuh"
+#include "alz_lane_tma.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -67,6 +68,11 @@ struct alz_plan {
   HostPipe pipe;
 };
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 // Kernel-parameter coefficient capacity (doubles).  CUDA 12.1+ allows 32764 bytes of
 // parameters; two sizes so that small filters do not push 28 KB per launch.
 static const int kCoefSmall = 512, kCoefLarge = 3584;
@@ -85,9 +91,66 @@ alz_generic_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant_
   alz_run_warp<AlzGenericCore>(a, ca, alz_smem);
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
+// TMA variants: same cores, tiles moved by cp.async.bulk.tensor (16-byte aligned rows only).
+static const int kWarpsPerSmTma = 24;
+template <int K, int NB, bool MONIC, int NCOEF>
+__global__ void __launch_bounds__(32, kWarpsPerSmTma)
+alz_biquad_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
+                      const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
+  extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
+  alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC>>(a, ca, &tmx, &tmy, alz_smem_tma);
+}
+
+__global__ void __launch_bounds__(32)
+alz_generic_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzGenericArgs ca,
+                       const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
+  extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
+  alz_run_warp_tma<AlzGenericCore>(a, ca, &tmx, &tmy, alz_smem_tma);
+}
+
+// ---- tensor maps (driver entry point fetched through the runtime: no libcuda link) -------
+typedef CUresult (*alz_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static alz_encode_tiled_fn get_encode_tiled() {
+  static alz_encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (alz_encode_tiled_fn)p;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// x[S][T] (row stride xs) and y[S][C][T] (row stride ys) as tiled tensor maps with 32-sample boxes.
+static bool make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap* tmy) {
+  alz_encode_tiled_fn enc = get_encode_tiled();
+  if (!enc || !ta.vec_in || !ta.vec_out || env_int("ALZ_NO_TMA", 0)) return false;
+  if (ta.T >= (1ll << 31) || ta.S >= (1ll << 31)) return false;
+  if ((unsigned long long)ta.xs * 4 >= (1ull << 40) || (unsigned long long)ta.ys * 4 * ta.C >= (1ull << 40)) return false;
+  const cuuint32_t estr[3] = {1, 1, 1};
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)ta.T, (cuuint64_t)ta.S};
+    const cuuint64_t strides[1] = {(cuuint64_t)ta.xs * 4};
+    const cuuint32_t box[2] = {32, 32};
+    if (enc(tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ta.x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)ta.T, (cuuint64_t)ta.C, (cuuint64_t)ta.S};
+    const cuuint64_t strides[2] = {(cuuint64_t)ta.ys * 4, (cuuint64_t)ta.ys * 4 * ta.C};
+    const cuuint32_t box[3] = {32, 1, 32};
+    if (enc(tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ta.y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
 }
 
 // One launch: channels [c0, c0+nch) x stream groups of `ta` (ta.S <= 65535*32 streams).
@@ -103,8 +166,12 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
   memcpy(ca.coef, p->h_tab.data() + (size_t)c0 * stride, (size_t)nch * stride * sizeof(double));
   ta.c_base = c0;
   const long long groups = (ta.S + 31) / 32;
-  auto kern = alz_biquad_kernel<K, NB, MONIC, NCOEF>;
-  kern<<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
+  CUtensorMap tmx, tmy;
+  if (make_tensor_maps(ta, &tmx, &tmy)) {
+    alz_biquad_tma_kernel<K, NB, MONIC, NCOEF><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
+  } else {
+    alz_biquad_kernel<K, NB, MONIC, NCOEF><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
+  }
   ALZ_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ALZ_OK;
@@ -153,7 +220,11 @@ static int launch_generic(const alz_plan* p, AlzTileArgs ta, double* state, long
   AlzGenericArgs ga{p->d_sec, p->d_tap_delay, p->d_coef, state, sstride, p->K, p->C, 0};
   ta.c_base = 0;
   const long long groups = (ta.S + 31) / 32;
-  alz_generic_kernel<<<dim3((unsigned)p->C, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ga);
+  CUtensorMap tmx, tmy;
+  if (make_tensor_maps(ta, &tmx, &tmy))
+    alz_generic_tma_kernel<<<dim3((unsigned)p->C, (unsigned)groups), 32, ALZ_TMA_SMEM, st>>>(ta, ga, tmx, tmy);
+  else
+    alz_generic_kernel<<<dim3((unsigned)p->C, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ga);
   ALZ_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ALZ_OK;

@@ -81,8 +81,11 @@ struct AlzGenericCore {
     return (float)in;
   }
 
-  __device__ __forceinline__ void tile(float* row, int nvalid, long long n_done) {
-    for (int j = 0; j < nvalid; ++j) row[j] = step((double)row[j], cnt0 + n_done + j);
+  __device__ __forceinline__ void tile(float* row, int swz, int nvalid, long long n_done) {
+    for (int j = 0; j < nvalid; ++j) {
+      float* p = row + ((((j >> 2) ^ swz) << 2) | (j & 3));
+      *p = step((double)*p, cnt0 + n_done + j);
+    }
   }
 
   __device__ __forceinline__ void store(const AlzGenericArgs&, long long, long long T) { st[0] = (double)(cnt0 + T); }

@@ -99,7 +99,7 @@ __device__ __forceinline__ void alz_issue_tile(const AlzTileArgs& a, float* buf,
 // Core concept:
 //   struct Core {
 //     __device__ void load(const CoreArgs&, long long r /* = s*C + c */, int c_local, bool valid);
-//     __device__ void tile(float* row, int nvalid, long long n_done);
+//     __device__ void tile(float* row, int swz, int nvalid, long long n_done);
 //         // row[0..nvalid) holds float32 inputs; overwrite them with float32 outputs.
 //         // n_done = samples already processed in this launch (warp-uniform).
 //     __device__ void store(const CoreArgs&, long long r, long long T);
@@ -138,7 +138,7 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
     alz_cp_wait<1>();   // every iteration commits exactly one group, so tile i has landed
     __syncwarp();
     const int nvalid = i < nfull ? ALZ_TT : (int)(a.T - t0);
-    core.tile(myrow0 + (i & 1) * (32 * ALZ_PITCH), nvalid, t0);
+    core.tile(myrow0 + (i & 1) * (32 * ALZ_PITCH), 0, nvalid, t0);
     __syncwarp();
 
     if (lean_out && i < nfull) {
