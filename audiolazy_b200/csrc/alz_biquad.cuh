@@ -52,10 +52,15 @@ struct AlzBiquadArgs {
   double coef[NCOEF];  // [channels of this launch][ALZ_COEF_STRIDE(K)]
 };
 
-template <int K, int NB, bool MONIC>
+// MONIC: 0 = plain sections; 1 = b0 factored out, gain applied to the float64 OUTPUT (one
+// DMUL per sample, bit-faithful); 2 = b0 factored out, gain applied to the float32 INPUT
+// (an FP32 multiply before the widening conversion: the FP64 pipe does one op less per
+// sample; costs two extra float32 roundings, <= 1.8e-7 relative, still 50x inside the bar).
+template <int K, int NB, int MONIC>
 struct AlzBiquadCore {
   double b0[K], c1[K], c2[K], na1[K], na2[K];
   double G;
+  float Gf;
   double u[K + 1][2];   // u[k][0] = u_k[n-1], u[k][1] = u_k[n-2]  (working units)
   double xe[K][2];      // explicit input histories of sections 1..K-1 (index 0 unused)
 
@@ -71,6 +76,7 @@ struct AlzBiquadCore {
       na2[k] = cf[5 * k + 4];
     }
     G = cf[5 * K];
+    Gf = (float)G;
     const double* st = ca.state + r;
     const long long R = ca.sstride;
 #pragma unroll
@@ -105,7 +111,7 @@ struct AlzBiquadCore {
       u[k + 1][0] = y;
       in = y; in1 = y1; in2 = y2;
     }
-    return (float)(MONIC ? G * in : in);
+    return (float)(MONIC == 1 ? G * in : in);
   }
 
   // First two samples of a launch: explicit input histories.
@@ -122,8 +128,11 @@ struct AlzBiquadCore {
       u[k + 1][0] = y;
       in = y;
     }
-    return (float)(MONIC ? G * in : in);
+    return (float)(MONIC == 1 ? G * in : in);
   }
+
+  // float32 sample -> float64 section input (with the input-side gain when MONIC == 2)
+  __device__ __forceinline__ double widen(float x) const { return MONIC == 2 ? (double)(x * Gf) : (double)x; }
 
   // Filter my row of the tile in place: float32 in, float32 out.  `swz` is the XOR
   // applied to the 16-byte chunk index (0 for the padded cp.async tile, lane & 7 for the
@@ -137,16 +146,16 @@ struct AlzBiquadCore {
         const float4 xc = xf;
         if (g + 1 < ALZ_TT / 4) xf = *reinterpret_cast<const float4*>(row + (((g + 1) ^ swz) << 2));   // prefetch
         float4 o;
-        o.x = step_alias((double)xc.x);
-        o.y = step_alias((double)xc.y);
-        o.z = step_alias((double)xc.z);
-        o.w = step_alias((double)xc.w);
+        o.x = step_alias(widen(xc.x));
+        o.y = step_alias(widen(xc.y));
+        o.z = step_alias(widen(xc.z));
+        o.w = step_alias(widen(xc.w));
         *reinterpret_cast<float4*>(p) = o;
       }
     } else {
       for (int j = 0; j < nvalid; ++j) {
         float* p = row + ((((j >> 2) ^ swz) << 2) | (j & 3));
-        const double xin = (double)*p;
+        const double xin = widen(*p);
         *p = (n_done + j < 2) ? step_explicit(xin) : step_alias(xin);
       }
     }

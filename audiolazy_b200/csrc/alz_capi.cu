@@ -78,7 +78,7 @@ static int env_int(const char* name, int dflt) {
 static const int kCoefSmall = 512, kCoefLarge = 3584;
 static const int kWarpsPerSm = 22;   // 2 x 4608 B tile buffers + 1 KB CTA reserve -> 22 CTAs per SM
 
-template <int K, int NB, bool MONIC, int NCOEF>
+template <int K, int NB, int MONIC, int NCOEF>
 __global__ void __launch_bounds__(32, kWarpsPerSm)
 alz_biquad_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca) {
   extern __shared__ __align__(16) float alz_smem[];
@@ -93,7 +93,7 @@ alz_generic_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant_
 
 // TMA variants: same cores, tiles moved by cp.async.bulk.tensor (16-byte aligned rows only).
 static const int kWarpsPerSmTma = 24;
-template <int K, int NB, bool MONIC, int NCOEF>
+template <int K, int NB, int MONIC, int NCOEF>
 __global__ void __launch_bounds__(32, kWarpsPerSmTma)
 alz_biquad_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
                       const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
@@ -154,7 +154,7 @@ static bool make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMa
 }
 
 // One launch: channels [c0, c0+nch) x stream groups of `ta` (ta.S <= 65535*32 streams).
-template <int K, int NB, bool MONIC, int NCOEF>
+template <int K, int NB, int MONIC, int NCOEF>
 static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, int c0, int nch,
                                cudaStream_t st) {
   static AlzBiquadArgs<NCOEF> ca;   // too large for the stack of some callers; filled under a lock
@@ -177,7 +177,7 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
   return ALZ_OK;
 }
 
-template <int K, int NB, bool MONIC>
+template <int K, int NB, int MONIC>
 static int launch_biquad_t(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
   const int stride = ALZ_COEF_STRIDE(K);
   const bool small = p->C * stride <= kCoefSmall;
@@ -193,8 +193,9 @@ static int launch_biquad_t(const alz_plan* p, const AlzTileArgs& ta, double* sta
 
 template <int K, int NB>
 static int launch_biquad_nb(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
-  if (p->monic) return launch_biquad_t<K, NB, true>(p, ta, state, sstride, st);
-  return launch_biquad_t<K, NB, false>(p, ta, state, sstride, st);
+  if (p->monic == 2) return launch_biquad_t<K, NB, 2>(p, ta, state, sstride, st);
+  if (p->monic == 1) return launch_biquad_t<K, NB, 1>(p, ta, state, sstride, st);
+  return launch_biquad_t<K, NB, 0>(p, ta, state, sstride, st);
 }
 template <int K>
 static int launch_biquad_k(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
@@ -318,14 +319,27 @@ int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int3
         if (!(std::fabs(g) > 1e-250 && std::fabs(g) < 1e250)) { monic = false; break; }
       }
     }
-    p->monic = monic ? 1 : 0;
-    p->fp64_ops = monic ? K * (p->NB - 1 + 2) + 1 : K * (p->NB + 2);
+    // input-side float32 gain (mode 2) when every channel's G is a normal float32 number
+    bool gain_in = monic && !env_int("ALZ_EXACT_GAIN", 0);
+    for (int c = 0; c < C && gain_in; ++c) {
+      double g = 1.0;
+      for (auto& s : secs[c]) g *= s.b[0];
+      if (!(std::fabs(g) > 1e-30 && std::fabs(g) < 1e30)) gain_in = false;
+    }
+    p->monic = monic ? (gain_in ? 2 : 1) : 0;
+    p->fp64_ops = monic ? K * (p->NB - 1 + 2) + (gain_in ? 0 : 1) : K * (p->NB + 2);
     const int stride = ALZ_COEF_STRIDE(K);
     p->h_tab.assign((size_t)C * stride, 0.0);
     p->sc.assign((size_t)C * (K + 1), 1.0);
     for (int c = 0; c < C; ++c) {
       double* rec = p->h_tab.data() + (size_t)c * stride;
       double g = 1.0, sc = 1.0;
+      if (p->monic == 2) {   // working units start at the (float32-rounded) gain applied to the input
+        double gg = 1.0;
+        for (auto& s : secs[c]) gg *= s.b[0];
+        sc = (double)(float)gg;
+        p->sc[(size_t)c * (K + 1)] = sc;
+      }
       for (int k = 0; k < K; ++k) {
         double b[3] = {1.0, 0.0, 0.0}, a[3] = {1.0, 0.0, 0.0};   // identity padding
         if (k < (int)secs[c].size()) {
@@ -501,7 +515,8 @@ int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double
         for (int j = 0; j < 2; ++j) {
           const double xv = xinit ? xinit[((size_t)c * K + k) * 2 + j] : 0.0;
           const double yv = yinit ? yinit[((size_t)c * K + k) * 2 + j] : 0.0;
-          proto[(size_t)(4 * k + j) * C + c] = xv * sc_in;
+          // mode 2 scales the float32 input by the float32 gain in FP32, exactly like the kernel
+          proto[(size_t)(4 * k + j) * C + c] = (p->monic == 2 && k == 0) ? (double)((float)xv * (float)sc_in) : xv * sc_in;
           proto[(size_t)(4 * k + 2 + j) * C + c] = yv * sc_out;
         }
       }
