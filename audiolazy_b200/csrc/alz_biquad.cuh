@@ -41,10 +41,14 @@
 constexpr int kAlzGroupUnroll = ALZ_GROUP_UNROLL;
 
 // Per-channel coefficient record inside the kernel parameters (constant bank):
-//   [k*5 + 0..4] = b0 (1 when monic), b1|c1, b2|c2, -a1, -a2   (all / a0);  [5K] = G.
-#define ALZ_COEF_STRIDE(K) (5 * (K) + 1)
-// State: state[slot * sstride + r], r = s*C + c, slots 4k+0..3 = xd1, xd2, yd1, yd2 of
-// section k (working units).
+//   [k*5 + 0..4] = b0 (1 when monic), b1|c1, b2|c2, -a1, -a2   (all / a0);  [5K] = G;
+//   head-FIR plans (NB0 = 8): [5K+1 .. 5K+5] = taps 3..7 of the FIRST section.
+#define ALZ_COEF_STRIDE(K, NB0) (5 * (K) + 1 + ((NB0) > 3 ? (NB0) - 3 : 0))
+// State: state[slot * sstride + r], r = s*C + c (working units).  Section 0: H0 input
+// delays (H0 = max(NB0 - 1, 2)) then yd1, yd2; section k >= 1: xd1, xd2, yd1, yd2.
+#define ALZ_H0(NB0) ((NB0) > 3 ? (NB0) - 1 : 2)
+#define ALZ_STATE_BASE(k, NB0) ((k) == 0 ? 0 : ALZ_H0(NB0) + 2 + 4 * ((k) - 1))
+#define ALZ_STATE_SLOTS(K, NB0) (ALZ_H0(NB0) + 2 + 4 * ((K) - 1))
 template <int NCOEF>
 struct AlzBiquadArgs {
   double* state;
@@ -56,17 +60,23 @@ struct AlzBiquadArgs {
 // DMUL per sample, bit-faithful); 2 = b0 factored out, gain applied to the float32 INPUT
 // (an FP32 multiply before the widening conversion: the FP64 pipe does one op less per
 // sample; costs two extra float32 roundings, <= 1.8e-7 relative, still 50x inside the bar).
-template <int K, int NB, int MONIC>
+// NB0: numerator taps of the FIRST section when it is longer than a biquad's (head FIR on
+// the input, e.g. gammatone.sampled's 8-tap first section); 0 = same as NB.
+template <int K, int NB, int MONIC, int NB0 = 0>
 struct AlzBiquadCore {
+  static constexpr int H0 = ALZ_H0(NB0);
+  static constexpr int NBF = NB0 > 3 ? NB0 : NB;   // taps of section 0
   double b0[K], c1[K], c2[K], na1[K], na2[K];
+  double ch[NB0 > 3 ? NB0 - 3 : 1];                // taps 3.. of section 0
   double G;
   float Gf;
-  double u[K + 1][2];   // u[k][0] = u_k[n-1], u[k][1] = u_k[n-2]  (working units)
+  double u[K + 1][2];   // u[k][0] = u_k[n-1], u[k][1] = u_k[n-2]; u[0] = input history (NB0 <= 3)
+  double xh[H0];        // input history of section 0 when NB0 > 3 (xh[j] = x[n-1-j])
   double xe[K][2];      // explicit input histories of sections 1..K-1 (index 0 unused)
 
   template <class Args>
   __device__ __forceinline__ void load(const Args& ca, long long r, int c_local, bool /*valid*/) {
-    const double* cf = ca.coef + c_local * ALZ_COEF_STRIDE(K);   // CTA-uniform address
+    const double* cf = ca.coef + c_local * ALZ_COEF_STRIDE(K, NB0);   // CTA-uniform address
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       b0[k] = cf[5 * k + 0];
@@ -77,16 +87,44 @@ struct AlzBiquadCore {
     }
     G = cf[5 * K];
     Gf = (float)G;
+    if (NB0 > 3) {
+#pragma unroll
+      for (int j = 3; j < NB0; ++j) ch[j - 3] = cf[5 * K + 1 + (j - 3)];
+    }
     const double* st = ca.state + r;
     const long long R = ca.sstride;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const double x1 = st[(4 * k + 0) * R], x2 = st[(4 * k + 1) * R];
-      if (k == 0) { u[0][0] = x1; u[0][1] = x2; xe[0][0] = xe[0][1] = 0.0; }
-      else { xe[k][0] = x1; xe[k][1] = x2; }
-      u[k + 1][0] = st[(4 * k + 2) * R];
-      u[k + 1][1] = st[(4 * k + 3) * R];
+    for (int j = 0; j < H0; ++j) xh[j] = st[(long long)j * R];
+    u[0][0] = xh[0]; u[0][1] = xh[1];
+    xe[0][0] = xe[0][1] = 0.0;
+    u[1][0] = st[(long long)(H0 + 0) * R];
+    u[1][1] = st[(long long)(H0 + 1) * R];
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      const int base = ALZ_STATE_BASE(k, NB0);
+      xe[k][0] = st[(long long)(base + 0) * R];
+      xe[k][1] = st[(long long)(base + 1) * R];
+      u[k + 1][0] = st[(long long)(base + 2) * R];
+      u[k + 1][1] = st[(long long)(base + 3) * R];
     }
+  }
+
+  // Section 0 with a head FIR: reads and shifts the input history xh.
+  __device__ __forceinline__ double head(double in) {
+    double t = MONIC ? in : b0[0] * in;
+    t = fma(c1[0], xh[0], t);
+    t = fma(c2[0], xh[1], t);
+#pragma unroll
+    for (int j = 3; j < NB0; ++j) t = fma(ch[j - 3], xh[j - 1], t);
+#pragma unroll
+    for (int j = H0 - 1; j > 0; --j) xh[j] = xh[j - 1];
+    xh[0] = in;
+    const double y1 = u[1][0], y2 = u[1][1];
+    t = fma(na2[0], y2, t);
+    const double y = fma(na1[0], y1, t);
+    u[1][1] = y1;
+    u[1][0] = y;
+    return y;
   }
 
   // One section's arithmetic.  in/in1/in2 = u_{k-1}[n], [n-1], [n-2].
@@ -100,11 +138,17 @@ struct AlzBiquadCore {
 
   // Steady state: section k reads the history of section k-1's output.
   __device__ __forceinline__ float step_alias(double xin) {
-    double in = xin, in1 = u[0][0], in2 = u[0][1];
-    u[0][1] = in1;
-    u[0][0] = in;
+    double in = xin, in1, in2;
+    if (NB0 > 3) {
+      in1 = u[1][0]; in2 = u[1][1];       // section 1 reads section 0's OLD output history
+      in = head(xin);
+    } else {
+      in1 = u[0][0]; in2 = u[0][1];
+      u[0][1] = in1;
+      u[0][0] = in;
+    }
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+    for (int k = (NB0 > 3 ? 1 : 0); k < K; ++k) {
       const double y1 = u[k + 1][0], y2 = u[k + 1][1];
       const double y = section(k, in, in1, in2, y1, y2);
       u[k + 1][1] = y1;
@@ -117,8 +161,9 @@ struct AlzBiquadCore {
   // First two samples of a launch: explicit input histories.
   __device__ __forceinline__ float step_explicit(double xin) {
     double in = xin;
+    if (NB0 > 3) in = head(xin);
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+    for (int k = (NB0 > 3 ? 1 : 0); k < K; ++k) {
       double in1, in2;
       if (k == 0) { in1 = u[0][0]; in2 = u[0][1]; u[0][1] = in1; u[0][0] = in; }
       else { in1 = xe[k][0]; in2 = xe[k][1]; xe[k][1] = in1; xe[k][0] = in; }
@@ -165,15 +210,25 @@ struct AlzBiquadCore {
   __device__ __forceinline__ void store(const Args& ca, long long r, long long T) {
     double* st = ca.state + r;
     const long long R = ca.sstride;
+    if (NB0 > 3) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
+      for (int j = 0; j < H0; ++j) st[(long long)j * R] = xh[j];
+    } else {
+      st[0] = u[0][0];
+      st[R] = u[0][1];
+    }
+    st[(long long)(H0 + 0) * R] = u[1][0];
+    st[(long long)(H0 + 1) * R] = u[1][1];
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      const int base = ALZ_STATE_BASE(k, NB0);
       double x1, x2;
-      if (k == 0 || T >= 2) { x1 = u[k][0]; x2 = u[k][1]; }   // aliased (or the input itself)
+      if (T >= 2) { x1 = u[k][0]; x2 = u[k][1]; }   // aliased: section k-1's output history
       else { x1 = xe[k][0]; x2 = xe[k][1]; }
-      st[(4 * k + 0) * R] = x1;
-      st[(4 * k + 1) * R] = x2;
-      st[(4 * k + 2) * R] = u[k + 1][0];
-      st[(4 * k + 3) * R] = u[k + 1][1];
+      st[(long long)(base + 0) * R] = x1;
+      st[(long long)(base + 1) * R] = x2;
+      st[(long long)(base + 2) * R] = u[k + 1][0];
+      st[(long long)(base + 3) * R] = u[k + 1][1];
     }
   }
 };

@@ -51,7 +51,7 @@ struct HostPipe {   // lazily created resources of alz_apply_f32_host
 };
 
 struct alz_plan {
-  int kind = 0, C = 0, K = 0, NB = 0, monic = 0, device = 0;
+  int kind = 0, C = 0, K = 0, NB = 0, NB0 = 0, monic = 0, device = 0;
   int xd = 0, yd = 0;          // history depths exposed to alz_state_init
   int state_doubles = 0;       // per recurrence
   int fp64_ops = 0;
@@ -78,11 +78,11 @@ static int env_int(const char* name, int dflt) {
 static const int kCoefSmall = 512, kCoefLarge = 3584;
 static const int kWarpsPerSm = 22;   // 2 x 4608 B tile buffers + 1 KB CTA reserve -> 22 CTAs per SM
 
-template <int K, int NB, int MONIC, int NCOEF>
+template <int K, int NB, int MONIC, int NCOEF, int NB0>
 __global__ void __launch_bounds__(32, kWarpsPerSm)
 alz_biquad_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca) {
   extern __shared__ __align__(16) float alz_smem[];
-  alz_run_warp<AlzBiquadCore<K, NB, MONIC>>(a, ca, alz_smem);
+  alz_run_warp<AlzBiquadCore<K, NB, MONIC, NB0>>(a, ca, alz_smem);
 }
 
 __global__ void __launch_bounds__(32)
@@ -93,12 +93,12 @@ alz_generic_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant_
 
 // TMA variants: same cores, tiles moved by cp.async.bulk.tensor (16-byte aligned rows only).
 static const int kWarpsPerSmTma = 24;
-template <int K, int NB, int MONIC, int NCOEF>
+template <int K, int NB, int MONIC, int NCOEF, int NB0>
 __global__ void __launch_bounds__(32, kWarpsPerSmTma)
 alz_biquad_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
                       const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
   extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
-  alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC>>(a, ca, &tmx, &tmy, alz_smem_tma);
+  alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0>>(a, ca, &tmx, &tmy, alz_smem_tma);
 }
 
 __global__ void __launch_bounds__(32)
@@ -154,7 +154,7 @@ static bool make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMa
 }
 
 // One launch: channels [c0, c0+nch) x stream groups of `ta` (ta.S <= 65535*32 streams).
-template <int K, int NB, int MONIC, int NCOEF>
+template <int K, int NB, int MONIC, int NCOEF, int NB0>
 static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, int c0, int nch,
                                cudaStream_t st) {
   static AlzBiquadArgs<NCOEF> ca;   // too large for the stack of some callers; filled under a lock
@@ -162,50 +162,61 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
   std::lock_guard<std::mutex> lock(mu);
   ca.state = state;
   ca.sstride = sstride;
-  const int stride = ALZ_COEF_STRIDE(K);
+  const int stride = ALZ_COEF_STRIDE(K, NB0);
   memcpy(ca.coef, p->h_tab.data() + (size_t)c0 * stride, (size_t)nch * stride * sizeof(double));
   ta.c_base = c0;
   const long long groups = (ta.S + 31) / 32;
   CUtensorMap tmx, tmy;
   if (make_tensor_maps(ta, &tmx, &tmy)) {
-    alz_biquad_tma_kernel<K, NB, MONIC, NCOEF><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
+    alz_biquad_tma_kernel<K, NB, MONIC, NCOEF, NB0><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
   } else {
-    alz_biquad_kernel<K, NB, MONIC, NCOEF><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
+    alz_biquad_kernel<K, NB, MONIC, NCOEF, NB0><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
   }
   ALZ_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ALZ_OK;
 }
 
-template <int K, int NB, int MONIC>
+template <int K, int NB, int MONIC, int NB0>
 static int launch_biquad_t(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
-  const int stride = ALZ_COEF_STRIDE(K);
+  const int stride = ALZ_COEF_STRIDE(K, NB0);
   const bool small = p->C * stride <= kCoefSmall;
   const int per_launch = (small ? kCoefSmall : kCoefLarge) / stride;
   for (int c0 = 0; c0 < p->C; c0 += per_launch) {
     const int nch = std::min(per_launch, p->C - c0);
-    const int rc = small ? launch_biquad_chunk<K, NB, MONIC, kCoefSmall>(p, ta, state, sstride, c0, nch, st)
-                         : launch_biquad_chunk<K, NB, MONIC, kCoefLarge>(p, ta, state, sstride, c0, nch, st);
+    const int rc = small ? launch_biquad_chunk<K, NB, MONIC, kCoefSmall, NB0>(p, ta, state, sstride, c0, nch, st)
+                         : launch_biquad_chunk<K, NB, MONIC, kCoefLarge, NB0>(p, ta, state, sstride, c0, nch, st);
     if (rc != ALZ_OK) return rc;
   }
   return ALZ_OK;
 }
 
-template <int K, int NB>
+template <int K, int NB, int NB0>
 static int launch_biquad_nb(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
-  if (p->monic == 2) return launch_biquad_t<K, NB, 2>(p, ta, state, sstride, st);
-  if (p->monic == 1) return launch_biquad_t<K, NB, 1>(p, ta, state, sstride, st);
-  return launch_biquad_t<K, NB, 0>(p, ta, state, sstride, st);
+  if (p->monic == 2) return launch_biquad_t<K, NB, 2, NB0>(p, ta, state, sstride, st);
+  if (p->monic == 1) return launch_biquad_t<K, NB, 1, NB0>(p, ta, state, sstride, st);
+  return launch_biquad_t<K, NB, 0, NB0>(p, ta, state, sstride, st);
 }
 template <int K>
 static int launch_biquad_k(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
   switch (p->NB) {
-    case 1: return launch_biquad_nb<K, 1>(p, ta, state, sstride, st);
-    case 2: return launch_biquad_nb<K, 2>(p, ta, state, sstride, st);
-    default: return launch_biquad_nb<K, 3>(p, ta, state, sstride, st);
+    case 1: return launch_biquad_nb<K, 1, 0>(p, ta, state, sstride, st);
+    case 2: return launch_biquad_nb<K, 2, 0>(p, ta, state, sstride, st);
+    default: return launch_biquad_nb<K, 3, 0>(p, ta, state, sstride, st);
   }
 }
+// head-FIR plans: first section with up to 8 numerator taps (K in {1, 4}, NB in {1, 3})
+template <int K>
+static int launch_headfir_k(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
+  if (p->NB <= 1) return launch_biquad_nb<K, 1, 8>(p, ta, state, sstride, st);
+  return launch_biquad_nb<K, 3, 8>(p, ta, state, sstride, st);
+}
 static int launch_biquad(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
+  if (p->NB0 == 8) {
+    if (p->K == 1) return launch_headfir_k<1>(p, ta, state, sstride, st);
+    if (p->K == 4) return launch_headfir_k<4>(p, ta, state, sstride, st);
+    return fail(ALZ_ERR_UNSUPPORTED, "no head-FIR kernel for K=%d", p->K);
+  }
   switch (p->K) {
     case 1: return launch_biquad_k<1>(p, ta, state, sstride, st);
     case 2: return launch_biquad_k<2>(p, ta, state, sstride, st);
@@ -299,15 +310,26 @@ int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int3
   p->C = C;
   p->device = dev;
 
-  const bool biquad = nbmax <= 3 && namax <= 3 && Kmax <= 8;
+  // numerator taps of the first section vs. of the later ones
+  int nb_first = 1, nb_rest = 1;
+  for (int c = 0; c < C; ++c)
+    for (size_t k = 0; k < secs[c].size(); ++k) {
+      if (k == 0) nb_first = std::max(nb_first, (int)secs[c][k].b.size());
+      else nb_rest = std::max(nb_rest, (int)secs[c][k].b.size());
+    }
+  const bool plain = nbmax <= 3 && namax <= 3 && Kmax <= 8;
+  const bool headfir = !plain && namax <= 3 && nb_first <= 8 && nb_rest <= 3 && Kmax <= 4;
+  const bool biquad = plain || headfir;
   if (biquad) {
     int K = 8;
     for (int kk : kBiquadKs) if (kk >= Kmax) { K = kk; break; }
+    if (headfir) K = Kmax == 1 ? 1 : 4;
     p->kind = ALZ_KIND_BIQUAD;
     p->K = K;
-    p->NB = nbmax;
-    p->xd = 2; p->yd = 2;
-    p->state_doubles = 4 * K;
+    p->NB = headfir ? (nb_rest <= 1 ? 1 : 3) : nbmax;
+    p->NB0 = headfir ? 8 : 0;
+    p->xd = ALZ_H0(p->NB0); p->yd = 2;
+    p->state_doubles = ALZ_STATE_SLOTS(K, p->NB0);
     // monic only if every b0 is a normal number and the running products stay normal
     bool monic = true;
     for (int c = 0; c < C && monic; ++c) {
@@ -327,8 +349,8 @@ int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int3
       if (!(std::fabs(g) > 1e-30 && std::fabs(g) < 1e30)) gain_in = false;
     }
     p->monic = monic ? (gain_in ? 2 : 1) : 0;
-    p->fp64_ops = monic ? K * (p->NB - 1 + 2) + (gain_in ? 0 : 1) : K * (p->NB + 2);
-    const int stride = ALZ_COEF_STRIDE(K);
+    p->fp64_ops = (monic ? K * (p->NB - 1 + 2) + (gain_in ? 0 : 1) : K * (p->NB + 2)) + (headfir ? 8 - p->NB : 0);
+    const int stride = ALZ_COEF_STRIDE(K, p->NB0);
     p->h_tab.assign((size_t)C * stride, 0.0);
     p->sc.assign((size_t)C * (K + 1), 1.0);
     for (int c = 0; c < C; ++c) {
@@ -341,13 +363,15 @@ int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int3
         p->sc[(size_t)c * (K + 1)] = sc;
       }
       for (int k = 0; k < K; ++k) {
-        double b[3] = {1.0, 0.0, 0.0}, a[3] = {1.0, 0.0, 0.0};   // identity padding
+        double b[8] = {1.0, 0, 0, 0, 0, 0, 0, 0}, a[3] = {1.0, 0.0, 0.0};   // identity padding
         if (k < (int)secs[c].size()) {
           const Sec& s = secs[c][k];
           b[0] = 0.0;
           for (size_t i = 0; i < s.b.size(); ++i) b[i] = s.b[i];
           for (size_t i = 0; i < s.a.size(); ++i) a[i] = s.a[i];
         }
+        if (k == 0 && p->NB0 == 8)
+          for (int j = 3; j < 8; ++j) rec[5 * K + 1 + (j - 3)] = monic ? b[j] / b[0] : b[j];
         if (monic) {
           rec[5 * k + 0] = 1.0;
           rec[5 * k + 1] = b[1] / b[0];
@@ -466,7 +490,7 @@ int32_t alz_plan_info_get(const alz_plan* p, alz_plan_info* out) {
   out->kind = p->kind;
   out->n_channels = p->C;
   out->n_sections = p->K;
-  out->num_taps = p->NB;
+  out->num_taps = p->NB0 ? p->NB0 : p->NB;
   out->monic = p->monic;
   out->state_doubles = p->state_doubles;
   out->fp64_ops = p->fp64_ops;
@@ -512,12 +536,16 @@ int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double
     for (int c = 0; c < C; ++c)
       for (int k = 0; k < K; ++k) {
         const double sc_in = p->sc[(size_t)c * (K + 1) + k], sc_out = p->sc[(size_t)c * (K + 1) + k + 1];
-        for (int j = 0; j < 2; ++j) {
-          const double xv = xinit ? xinit[((size_t)c * K + k) * 2 + j] : 0.0;
-          const double yv = yinit ? yinit[((size_t)c * K + k) * 2 + j] : 0.0;
+        const int base = ALZ_STATE_BASE(k, p->NB0);
+        const int nx = k == 0 ? ALZ_H0(p->NB0) : 2;
+        for (int j = 0; j < nx; ++j) {
+          const double xv = xinit ? xinit[((size_t)c * K + k) * p->xd + j] : 0.0;
           // mode 2 scales the float32 input by the float32 gain in FP32, exactly like the kernel
-          proto[(size_t)(4 * k + j) * C + c] = (p->monic == 2 && k == 0) ? (double)((float)xv * (float)sc_in) : xv * sc_in;
-          proto[(size_t)(4 * k + 2 + j) * C + c] = yv * sc_out;
+          proto[(size_t)(base + j) * C + c] = (p->monic == 2 && k == 0) ? (double)((float)xv * (float)sc_in) : xv * sc_in;
+        }
+        for (int j = 0; j < 2; ++j) {
+          const double yv = yinit ? yinit[((size_t)c * K + k) * 2 + j] : 0.0;
+          proto[(size_t)(base + nx + j) * C + c] = yv * sc_out;
         }
       }
   } else {

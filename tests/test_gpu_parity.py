@@ -52,7 +52,8 @@ def gpu():
 def test_bank_vs_golden_and_oracle(gpu, designs, vectors, name):
   bank = designs["bank_" + name]
   plan = gpu.capi.Plan(bank)
-  assert plan.kind == (gpu.capi.KIND_GENERIC if name == "sampled" else gpu.capi.KIND_BIQUAD)
+  assert plan.kind == gpu.capi.KIND_BIQUAD            # sampled: head-FIR variant (8-tap first section)
+  assert plan.num_taps == {"slaney": 2, "klapuri": 3, "sampled": 8}[name]
   x = np.stack([signal(0, 8000), signal(7, 8000), signal(8, 8000)])
   y = gpu.run(plan, x)
   assert rel_err(y[0][vectors["bank_channels"]], vectors["bank_%s_y" % name]) <= TOL      # the reference's own output
@@ -124,7 +125,7 @@ def test_ragged_shapes(gpu, designs, C, S, T):
 
 def test_block_split_is_bit_exact(gpu, designs):
   x = np.stack([signal(0, 8000), signal(7, 8000)])
-  for name in ("slaney", "klapuri"):
+  for name in ("slaney", "klapuri", "sampled"):
     plan = gpu.capi.Plan(designs["bank_" + name])
     y = gpu.run(plan, x)
     assert np.array_equal(gpu.run(plan, x, splits=[1, 1, 30, 33, 935, 7000]), y)
