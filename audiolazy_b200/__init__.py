@@ -17,5 +17,7 @@ from .filters import (LinearFilterProperties, LinearFilter, ZFilter, z, FilterLi
                       comb, resonator, lowpass, highpass)
 from .auditory import erb, gammatone, gammatone_erb_constants, erb_space, gammatone_bank
 from .bank import FilterBank, BankState
+from .callers import envelope, maverage, karplus_strong, accumulate_z, zeros, ones, impulse, white_noise
+from .io import chunks, WavStream, wav_batch, pcm_to_float32
 
 __version__ = "0.1.0"

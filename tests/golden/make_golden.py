@@ -130,6 +130,19 @@ def main():
   vectors["parallel_y"] = run(par, xs)
   designs["parallel"] = [sections_of(f) for f in par]
 
+  # ---------------------------------------------------------------- callers of the path
+  xc = signal(5, 3000)
+  xl = xc.astype(np.float64).tolist()
+  vectors["envelope_rms_y"] = np.array(list(al.envelope.rms(xl, cutoff=np.pi / 64)))
+  vectors["envelope_abs_y"] = np.array(list(al.envelope.abs(xl)))
+  vectors["envelope_squared_y"] = np.array(list(al.envelope.squared(xl, cutoff=0.2)))
+  vectors["maverage_recursive_y"] = run(al.maverage.recursive(16), xc)
+  vectors["maverage_fir_y"] = run(al.maverage.fir(5), xc)
+  mem = signal(6, 400).astype(np.float64).tolist()
+  ks = al.karplus_strong(2 * np.pi * 220.5 / 44100, tau=5e3, memory=mem)
+  vectors["karplus_strong_y"] = np.array(ks.take(3000))
+  vectors["accumulate_z_y"] = run(al.accumulate.z, signal(8, 500))
+
   # ---------------------------------------------------------------- builders (designs only)
   grid = []
   for name in ["poles_exp", "freq_poles_exp", "z_exp", "freq_z_exp"]:

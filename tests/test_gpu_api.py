@@ -162,3 +162,18 @@ def test_two_gpu_channel_sharding(ab):
     y1 = bank.apply(torch.from_numpy(x).cuda()).cpu().numpy()
   y0 = bank.apply(torch.from_numpy(x).cuda()).cpu().numpy()
   assert np.array_equal(y0, y1)
+
+
+def test_callers_of_the_path(ab, vectors):
+  """envelope / maverage / karplus_strong / accumulate, against outputs
+  of the reference's own implementations (tests/golden/make_golden.py)."""
+  xc = signal(5, 3000).tolist()
+  assert rel_err(list(ab.envelope.rms(xc, cutoff=np.pi / 64)), vectors["envelope_rms_y"]) <= TOL
+  assert rel_err(list(ab.envelope.abs(xc)), vectors["envelope_abs_y"]) <= TOL
+  assert rel_err(list(ab.envelope.squared(xc, cutoff=0.2)), vectors["envelope_squared_y"]) <= TOL
+  assert rel_err(list(ab.maverage.recursive(16)(xc)), vectors["maverage_recursive_y"]) <= TOL
+  assert rel_err(list(ab.maverage.fir(5)(xc)), vectors["maverage_fir_y"]) <= TOL
+  mem = signal(6, 400).astype(np.float64).tolist()
+  ks = ab.karplus_strong(2 * np.pi * 220.5 / 44100, tau=5e3, memory=mem)      # endless silence in, seeded comb
+  assert rel_err(ks.take(3000), vectors["karplus_strong_y"]) <= TOL
+  assert rel_err(list(ab.accumulate_z(signal(8, 500).tolist())), vectors["accumulate_z_y"]) <= TOL
