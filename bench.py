@@ -244,11 +244,21 @@ def run_ours(args):
   # ---- end to end through the host-buffer C-ABI entry ------------------------------------
   e2e = None
   if not args.no_e2e:
-    xh = torch.empty((S, Tn), dtype=torch.float32).pin_memory()
-    xh.copy_(x.cpu())
-    yh = torch.empty((S, C, Tn), dtype=torch.float32).pin_memory()
+    # pinned host buffers for the whole batch (17.4 GB per rank); shrink the e2e batch only if
+    # the box cannot pin that much for every rank
+    Se = S
+    try:
+      import psutil
+      avail = psutil.virtual_memory().available
+      per_stream = (C + 1) * Tn * 4
+      Se = int(max(32, min(S, (avail * 0.4 / world) // per_stream // 32 * 32)))
+    except Exception:
+      pass
+    xh = torch.empty((Se, Tn), dtype=torch.float32).pin_memory()
+    xh.copy_(x[:Se].cpu())
+    yh = torch.empty((Se, C, Tn), dtype=torch.float32).pin_memory()
     xn, yn = xh.numpy(), yh.numpy()
-    state.zero_()
+    state = torch.zeros(plan.state_doubles(Se), dtype=torch.float64, device=dev)
     plan.apply_host(xn, yn, state.data_ptr())                  # warm-up: allocates the staging buffers
     k_e2e = max(1, min(args.steps, 3))
     barrier()
@@ -259,9 +269,10 @@ def run_ours(args):
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if distributed:
       dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * S * Tn * k_e2e / float(dt.item()), "unit": UNIT,
-           "h2d_bytes_per_step": world * S * Tn * 4, "d2h_bytes_per_step": world * S * C * Tn * 4,
-           "steps": k_e2e, "note": "pinned host buffers, PCIe-bound on the 256 B/sample output"}
+    e2e = {"value": world * Se * Tn * k_e2e / float(dt.item()), "unit": UNIT,
+           "h2d_bytes_per_step": world * Se * Tn * 4, "d2h_bytes_per_step": world * Se * C * Tn * 4,
+           "steps": k_e2e, "streams_per_gpu": Se,
+           "note": "alz_apply_f32_host with pinned host buffers; PCIe-bound on the 256 B/sample output"}
     del xh, yh
 
   if rank == 0:
