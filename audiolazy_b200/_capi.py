@@ -22,10 +22,12 @@ ALZ_ERR_NOMEM = -5
 ALZ_ERR_UNSUPPORTED = -6
 KIND_BIQUAD = 1
 KIND_GENERIC = 2
+PLAN_FORCE_GENERIC = 1
 
 #: every symbol include/alz_b200.h declares (tests check the library exports them all)
 SYMBOLS = (
-  "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_destroy",
+  "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_create_ex",
+  "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32",
   "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
   "alz_apply_f32_host", "alz_sum_channels_f32", "alz_launch_count",
 )
@@ -67,6 +69,12 @@ def lib():
   L.alz_set_device.argtypes = [i32]
   L.alz_plan_create.restype = i32
   L.alz_plan_create.argtypes = [vp, vp, i32, i32, ctypes.POINTER(vp)]
+  L.alz_plan_create_ex.restype = i32
+  L.alz_plan_create_ex.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp)]
+  L.alz_plan_taps.restype = i32
+  L.alz_plan_taps.argtypes = [vp, vp, vp, i32]
+  L.alz_apply_tv_f32.restype = i32
+  L.alz_apply_tv_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, i64, vp]
   L.alz_plan_destroy.restype = None
   L.alz_plan_destroy.argtypes = [vp]
   L.alz_plan_info_get.restype = i32
@@ -119,11 +127,12 @@ def pack_sections(bank):
 class Plan(object):
   """A compiled bank of cascades living on the current CUDA device."""
 
-  def __init__(self, bank):
+  def __init__(self, bank, force_generic=False):
     L = lib()
     coef, desc, C, KM = pack_sections(bank)
     handle = ctypes.c_void_p()
-    _check(L.alz_plan_create(coef.ctypes.data, desc.ctypes.data, C, KM, ctypes.byref(handle)))
+    _check(L.alz_plan_create_ex(coef.ctypes.data, desc.ctypes.data, C, KM, PLAN_FORCE_GENERIC if force_generic else 0,
+                                ctypes.byref(handle)))
     self._h = handle
     info = PlanInfo()
     _check(L.alz_plan_info_get(self._h, ctypes.byref(info)))
@@ -160,6 +169,18 @@ class Plan(object):
   def apply(self, x_ptr, y_ptr, state_ptr, n_streams, n_samples, x_stride, y_stride, stream=0):
     _check(lib().alz_apply_f32(self._h, x_ptr, y_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),
                                int(y_stride), stream))
+
+  def taps(self):
+    """``[(delay, is_den), ...]`` in coefficient-table order (generic plans only)."""
+    n = _check(lib().alz_plan_taps(self._h, None, None, 0))
+    delay = np.zeros(n, dtype=np.int32)
+    is_den = np.zeros(n, dtype=np.int32)
+    _check(lib().alz_plan_taps(self._h, delay.ctypes.data, is_den.ctypes.data, n))
+    return list(zip(delay.tolist(), [bool(v) for v in is_den.tolist()]))
+
+  def apply_tv(self, x_ptr, y_ptr, state_ptr, n_streams, n_samples, x_stride, y_stride, coef_ptr, coef_stride, stream=0):
+    _check(lib().alz_apply_tv_f32(self._h, x_ptr, y_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),
+                                  int(y_stride), coef_ptr, int(coef_stride), stream))
 
   def apply_host(self, x, y=None, state_ptr=None):
     """``x``: float32 ndarray [S][T] (C-contiguous rows). Returns ``y`` [S][C][T]."""

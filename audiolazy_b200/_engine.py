@@ -187,3 +187,70 @@ def bank_streams(bank_sections, seq, xinit, yinit):
         yield value
 
   return [Stream(channel(c)) for c in range(C)]
+
+
+# --------------------------------------------------------------------------------------
+# time-varying coefficients (reference lazy_filters.py:169-176, 200-216, 262-263)
+# --------------------------------------------------------------------------------------
+def filter_stream_tv(num_terms, den_terms, seq, memory_init, zero):
+  """Lazy Stream of a single filter whose coefficients may be Streams.
+
+  ``num_terms`` / ``den_terms``: ``[(delay, coeff)]`` sorted by delay (``den_terms`` includes
+  delay 0); ``coeff`` is a number or an iterator advanced once per input sample. A Stream a0
+  becomes a variable gain exactly as the reference rewrites it: ``inv = 1 / a0`` and every
+  other coefficient is multiplied by ``inv``. The per-sample coefficient values of a block
+  are evaluated on the host (they are the USER's streams) and uploaded with the block."""
+  torch = torch_mod()
+  device = torch.device("cuda", torch.cuda.current_device())
+  _capi.set_device(device.index)
+  a0 = dict(den_terms)[0]
+  num = [(d, c) for d, c in num_terms]
+  den = [(d, c) for d, c in den_terms if d != 0]
+  sections = [([1.0 if any(d == k for d, _ in num) else 0.0 for k in range(max([d for d, _ in num] + [0]) + 1)] or [1.0],
+               [1.0] + [1.0 if any(d == k for d, _ in den) else 0.0 for k in range(1, max([d for d, _ in den] + [0]) + 1)])]
+  if not num:
+    sections[0] = ([0.0], sections[0][1])
+  plan = _capi.Plan([sections], force_generic=True)
+  taps = plan.taps()
+  sources = []
+  for delay, is_den in taps:
+    table = dict(den) if is_den else dict(num)
+    sources.append((is_den, table.get(delay, 0.0)))
+  state = torch.empty(max(1, plan.state_doubles(1)), dtype=torch.float64, device=device)
+  xi = np.zeros((1, 1, max(plan.xd, 1)))[:, :, :plan.xd]
+  yi = np.zeros((1, 1, max(plan.yd, 1)))[:, :, :plan.yd]
+  xi[...] = float(zero)
+  yi[0, 0, :len(memory_init)] = memory_init[:plan.yd]
+  cur = lambda: torch.cuda.current_stream(device).cuda_stream
+  plan.state_init(state.data_ptr(), 1, xi if plan.xd else None, yi if plan.yd else None, cur())
+
+  def pull(src, n):
+    if hasattr(src, "__next__"):
+      return list(it.islice(src, n))
+    return None    # constant
+
+  def gen():
+    for xb in _blocks(seq):
+      n = len(xb)
+      cols = [pull(src, n) for _, src in sources]
+      a0_vals = pull(a0, n)
+      lens = [len(c) for c in cols if c is not None] + ([len(a0_vals)] if a0_vals is not None else [])
+      m = min([n] + lens)           # the shortest coefficient stream ends the output (zip semantics)
+      if m == 0:
+        return
+      inv = None if a0_vals is None else 1.0 / np.asarray(a0_vals[:m], dtype=np.float64)
+      coef = np.empty((len(sources), m), dtype=np.float64)
+      for row, (col, (is_den, src)) in enumerate(zip(cols, sources)):
+        vals = np.full(m, float(src)) if col is None else np.asarray(col[:m], dtype=np.float64)
+        vals = vals * inv if inv is not None else vals / float(a0)
+        coef[row] = -vals if is_den else vals
+      x_dev = torch.from_numpy(np.ascontiguousarray(xb[:m])).to(device)
+      c_dev = torch.from_numpy(coef).to(device)
+      y_dev = torch.empty(m, dtype=torch.float32, device=device)
+      plan.apply_tv(x_dev.data_ptr(), y_dev.data_ptr(), state.data_ptr(), 1, m, m, m, c_dev.data_ptr(), m, cur())
+      for value in y_dev.cpu().numpy().tolist():
+        yield value
+      if m < n:
+        return
+
+  return Stream(gen())

@@ -64,6 +64,7 @@ struct alz_plan {
   std::vector<double> sc;                 // biquad: [C][K+1] working-unit scales
   std::vector<AlzGenSection> h_sec;       // generic
   std::vector<int> h_xlen, h_ylen;        // generic: true max delays per section
+  std::vector<int> h_tap_delay, h_tap_is_den;   // generic: tap order of the coefficient table
   std::mutex host_mu;
   HostPipe pipe;
 };
@@ -228,8 +229,9 @@ static int launch_biquad(const alz_plan* p, const AlzTileArgs& ta, double* state
   return fail(ALZ_ERR_UNSUPPORTED, "no biquad kernel for K=%d", p->K);
 }
 
-static int launch_generic(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, cudaStream_t st) {
-  AlzGenericArgs ga{p->d_sec, p->d_tap_delay, p->d_coef, state, sstride, p->K, p->C, 0};
+static int launch_generic(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, cudaStream_t st,
+                          const double* tv = nullptr, long long tv_stride = 0) {
+  AlzGenericArgs ga{p->d_sec, p->d_tap_delay, p->d_coef, state, sstride, p->K, p->C, 0, tv, tv_stride};
   ta.c_base = 0;
   const long long groups = (ta.S + 31) / 32;
   CUtensorMap tmx, tmy;
@@ -263,6 +265,11 @@ int32_t alz_set_device(int32_t device) {
 }
 
 int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int32_t KM, alz_plan** out) {
+  return alz_plan_create_ex(coef, desc, C, KM, 0, out);
+}
+
+int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, int32_t KM, int32_t flags,
+                           alz_plan** out) {
   if (!out) return fail(ALZ_ERR_INVALID, "out is null");
   *out = nullptr;
   if (!coef || !desc || C <= 0 || KM < 0) return fail(ALZ_ERR_INVALID, "bad plan arguments");
@@ -319,7 +326,7 @@ int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int3
     }
   const bool plain = nbmax <= 3 && namax <= 3 && Kmax <= 8;
   const bool headfir = !plain && namax <= 3 && nb_first <= 8 && nb_rest <= 3 && Kmax <= 4;
-  const bool biquad = plain || headfir;
+  const bool biquad = (plain || headfir) && !(flags & ALZ_PLAN_FORCE_GENERIC);
   if (biquad) {
     int K = 8;
     for (int kk : kBiquadKs) if (kk >= Kmax) { K = kk; break; }
@@ -419,7 +426,7 @@ int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int3
           col[c] = v;
           any = any || v != 0.0;
         }
-        if (any || d == 0) { tap_delay.push_back((int)d); tap_coef.push_back(std::move(col)); }
+        if (any || d == 0) { tap_delay.push_back((int)d); tap_coef.push_back(std::move(col)); p->h_tap_is_den.push_back(0); }
       }
       gs.nnum = (int)tap_delay.size() - gs.num_begin;
       gs.den_begin = (int)tap_delay.size();
@@ -431,7 +438,7 @@ int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int3
           col[c] = v;
           any = any || v != 0.0;
         }
-        if (any) { tap_delay.push_back((int)d); tap_coef.push_back(std::move(col)); }
+        if (any) { tap_delay.push_back((int)d); tap_coef.push_back(std::move(col)); p->h_tap_is_den.push_back(1); }
       }
       gs.nden = (int)tap_delay.size() - gs.den_begin;
       const int xlen = (int)nb - 1, ylen = (int)na - 1;
@@ -449,6 +456,7 @@ int32_t alz_plan_create(const double* coef, const int32_t* desc, int32_t C, int3
     p->state_doubles = slot;
     p->fp64_ops = ops;
     const size_t ntaps = tap_delay.size();
+    p->h_tap_delay = tap_delay;
     std::vector<double> tab(ntaps * C);
     for (size_t t = 0; t < ntaps; ++t) memcpy(&tab[t * C], tap_coef[t].data(), C * sizeof(double));
     cudaError_t e = cudaMalloc(&p->d_coef, tab.size() * sizeof(double));
@@ -575,7 +583,8 @@ int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double
 }
 
 static int apply_impl(const alz_plan* p, const float* x, float* y, double* state, long long sstride, long long S,
-                      long long T, long long xs, long long ys, cudaStream_t st) {
+                      long long T, long long xs, long long ys, cudaStream_t st, const double* tv = nullptr,
+                      long long tv_stride = 0) {
   AlzTileArgs ta{};
   ta.T = T; ta.xs = xs; ta.ys = ys; ta.C = p->C; ta.c_base = 0;
   ta.vec_in = (((uintptr_t)x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
@@ -587,7 +596,7 @@ static int apply_impl(const alz_plan* p, const float* x, float* y, double* state
     ta.y = y + s0 * p->C * ys;
     double* stp = state + s0 * p->C;
     const int rc = p->kind == ALZ_KIND_BIQUAD ? launch_biquad(p, ta, stp, sstride, st)
-                                               : launch_generic(p, ta, stp, sstride, st);
+                                               : launch_generic(p, ta, stp, sstride, st, tv, tv_stride);
     if (rc != ALZ_OK) return rc;
   }
   return ALZ_OK;
@@ -604,6 +613,34 @@ int32_t alz_apply_f32(const alz_plan* p, const float* x, float* y, double* state
   ALZ_CUDA(cudaGetDevice(&cur));
   if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
   const int rc = apply_impl(p, x, y, state, (long long)S * p->C, S, T, xs, ys, (cudaStream_t)cuda_stream);
+  if (cur != p->device) cudaSetDevice(cur);
+  return rc;
+}
+
+int32_t alz_plan_taps(const alz_plan* p, int32_t* delay, int32_t* is_den, int32_t cap) {
+  if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (p->kind != ALZ_KIND_GENERIC) return fail(ALZ_ERR_UNSUPPORTED, "tap list exists only for generic plans");
+  const int n = (int)p->h_tap_delay.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (delay) delay[i] = p->h_tap_delay[i];
+    if (is_den) is_den[i] = p->h_tap_is_den[i];
+  }
+  return n;
+}
+
+int32_t alz_apply_tv_f32(const alz_plan* p, const float* x, float* y, double* state, int64_t S, int64_t T,
+                         int64_t xs, int64_t ys, const double* coef_dev, int64_t coef_stride, void* cuda_stream) {
+  if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (p->kind != ALZ_KIND_GENERIC || p->C != 1)
+    return fail(ALZ_ERR_UNSUPPORTED, "time-varying coefficients need a single-channel generic plan (alz_plan_create_ex)");
+  if (S < 0 || T < 0) return fail(ALZ_ERR_INVALID, "negative size");
+  if (S == 0 || T == 0) return ALZ_OK;
+  if (!x || !y || !state || !coef_dev) return fail(ALZ_ERR_INVALID, "null buffer");
+  if (xs < T || ys < T || coef_stride < T) return fail(ALZ_ERR_INVALID, "row stride shorter than n_samples");
+  int cur = -1;
+  ALZ_CUDA(cudaGetDevice(&cur));
+  if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
+  const int rc = apply_impl(p, x, y, state, (long long)S, S, T, xs, ys, (cudaStream_t)cuda_stream, coef_dev, coef_stride);
   if (cur != p->device) cudaSetDevice(cur);
   return rc;
 }

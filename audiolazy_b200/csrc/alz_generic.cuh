@@ -33,6 +33,10 @@ struct AlzGenericArgs {
   int K;
   int C;
   int c_base;
+  // time-varying coefficients (reference lazy_filters.py:200-216): when non-null, tap i of
+  // sample j of THIS launch uses tv[i * tv_stride + j] instead of coef[i][c] (C must be 1)
+  const double* tv;
+  long long tv_stride;
 };
 
 struct AlzGenericCore {
@@ -43,6 +47,8 @@ struct AlzGenericCore {
   long long R;
   long long cnt0;
   int K, C;
+  const double* tv;
+  long long tv_stride;
   bool live;   // lanes beyond the last stream must not touch the (clamped) state rows
 
   __device__ __forceinline__ void load(const AlzGenericArgs& ca, long long r, int c_local, bool valid) {
@@ -54,10 +60,16 @@ struct AlzGenericCore {
     cf = ca.coef + (ca.c_base + c_local);
     st = ca.state + r;
     cnt0 = (long long)st[0];
+    tv = ca.tv;
+    tv_stride = ca.tv_stride;
     live = valid;
   }
 
-  __device__ __forceinline__ float step(double xin, long long n) {
+  __device__ __forceinline__ double coef_at(int tap, long long j) const {
+    return tv ? tv[(long long)tap * tv_stride + j] : cf[(long long)tap * C];
+  }
+
+  __device__ __forceinline__ float step(double xin, long long n, long long j) {
     double in = xin;
     for (int k = 0; k < K; ++k) {
       const AlzGenSection s = sec[k];
@@ -65,12 +77,12 @@ struct AlzGenericCore {
       for (int i = 0; i < s.nnum; ++i) {
         const int d = tap_delay[s.num_begin + i];
         const double v = d == 0 ? in : st[(long long)(s.xbase + (int)((n - d) & s.xmask)) * R];
-        acc = fma(cf[(long long)(s.num_begin + i) * C], v, acc);
+        acc = fma(coef_at(s.num_begin + i, j), v, acc);
       }
       for (int i = 0; i < s.nden; ++i) {
         const int d = tap_delay[s.den_begin + i];
         const double v = st[(long long)(s.ybase + (int)((n - d) & s.ymask)) * R];
-        acc = fma(cf[(long long)(s.den_begin + i) * C], v, acc);
+        acc = fma(coef_at(s.den_begin + i, j), v, acc);
       }
       if (live) {
         if (s.xmask >= 0) st[(long long)(s.xbase + (int)(n & s.xmask)) * R] = in;
@@ -84,7 +96,7 @@ struct AlzGenericCore {
   __device__ __forceinline__ void tile(float* row, int swz, int nvalid, long long n_done) {
     for (int j = 0; j < nvalid; ++j) {
       float* p = row + ((((j >> 2) ^ swz) << 2) | (j & 3));
-      *p = step((double)*p, cnt0 + n_done + j);
+      *p = step((double)*p, cnt0 + n_done + j, n_done + j);
     }
   }
 

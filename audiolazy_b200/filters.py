@@ -24,8 +24,10 @@ What differs from the reference, by design:
   typical), and are Python floats whatever the input type was.
 * input is pulled in blocks (read-ahead), not sample by sample.
 * time-varying coefficients (Stream-valued ``b_k`` / ``a_k``, reference
-  ``lazy_filters.py:200-216``) are not on the accelerated path yet and raise
-  ``NotImplementedError``.
+  ``lazy_filters.py:169-176, 200-216``): the coefficient Streams are the user's Python
+  iterables, so their per-sample values are pulled on the host block by block and uploaded
+  with the samples; the difference equation itself still runs in the CUDA kernel
+  (``alz_apply_tv_f32``).
 """
 from __future__ import annotations
 
@@ -156,16 +158,17 @@ class LinearFilter(LinearFilterProperties):
     terms = list(self.numpoly.terms()) + list(self.denpoly.terms())
     if any(power < 0 for power, _ in terms):
       raise ValueError("Non-causal filter")
-    if any(isinstance(c, Iterable) for _, c in terms):
-      raise NotImplementedError("time-varying (Stream-valued) coefficients are not on the accelerated path")
-    if self.denpoly[0] == 0:
+    a0 = self.denpoly[0]
+    if not isinstance(a0, Stream) and a0 == 0:
       raise ZeroDivisionError("Invalid filter gain")
-    if not all(_is_real_number(c) for _, c in terms):
-      raise NotImplementedError("only real-number coefficients run on the accelerated path")
+    if not all(isinstance(c, Stream) or _is_real_number(c) for _, c in terms):
+      raise NotImplementedError("only real-number (or Stream-of-number) coefficients run on the accelerated path")
 
   def sections(self):
     """``[(b, a)]``: this filter as one direct-form-I section (float lists)."""
     self._check_callable()
+    if not self.is_lti():
+      raise NotImplementedError("a time-varying filter has no constant section table")
     b = [float(v) for v in self.numlist] or [0.0]
     a = [float(v) for v in self.denlist]
     return [(b, a)]
@@ -176,6 +179,14 @@ class LinearFilter(LinearFilterProperties):
     ``memory`` seeds the output history (iterable: its first items; callable: called
     with the size), ``zero`` the input pre-history and missing memory entries."""
     from . import _engine
+    if not self.is_lti():
+      self._check_callable()
+      lm = max(p for p, _ in self.denpoly.terms())
+      _, yinit = _seed_histories([([0.0], [1.0] * (lm + 1))], memory, zero)
+      as_source = lambda c: iter(c) if isinstance(c, Stream) else c
+      num = [(p, as_source(c)) for p, c in self.numpoly.terms()]
+      den = [(p, as_source(c)) for p, c in self.denpoly.terms()]
+      return _engine.filter_stream_tv(num, den, seq, yinit[0], float(zero))
     sections = self.sections()
     xinit, yinit = _seed_histories(sections, memory, zero)
     return _engine.filter_stream([sections], seq, [xinit], [yinit])

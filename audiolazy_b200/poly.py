@@ -15,14 +15,19 @@ Semantics kept from the reference because results depend on them:
   fixes the floating-point summation order of every design formula;
 * ``terms()`` sorts by power, ``values()`` is the dense ascending list.
 
-Stream-valued (time-varying) coefficients, ``lagrange`` and ``resample`` are out of
-scope of the accelerated path and not provided.
+Coefficients may be :class:`~audiolazy_b200.stream.Stream` instances (time-varying
+filters): as in the reference they are kept whatever their values, compared by identity,
+tee-copied by :meth:`Poly.copy`, and fanned out with ``thub`` when a product or a division
+uses them more than once (``lazy_poly.py:388-402, 449-462``). ``lagrange`` and ``resample``
+are out of scope.
 """
 from __future__ import annotations
 
 import operator
 from collections.abc import Iterable
 from functools import reduce
+
+from .stream import Stream, thub
 
 __all__ = ["Poly", "x"]
 
@@ -48,6 +53,8 @@ class Poly(object):
       items = list(enumerate(data))
     elif data is None:
       items = []
+    elif isinstance(data, Stream):            # a (possibly endless) coefficient stream: constant term
+      items = [(0, data)]
     elif isinstance(data, Iterable) and not isinstance(data, (str, bytes)):
       items = list(enumerate(data))
     else:
@@ -56,7 +63,7 @@ class Poly(object):
     for power, coeff in items:
       if isinstance(power, float) and power.is_integer():
         power = int(power)
-      if not isinstance(coeff, Iterable) and coeff == self._zero:   # Stream coefficients are kept
+      if not isinstance(coeff, Stream) and coeff == self._zero:   # Stream coefficients are kept
         terms.pop(power, None)
         continue
       terms[power] = coeff
@@ -103,7 +110,9 @@ class Poly(object):
     return max(self._terms) if self._terms else 0
 
   def copy(self, zero=None):
-    return Poly(dict(self._terms), zero=self._zero if zero is None else zero)
+    """Same terms; Stream coefficients are tee-copied so both polynomials stay usable."""
+    return Poly({k: (v.copy() if isinstance(v, Stream) else v) for k, v in self._terms.items()},
+                zero=self._zero if zero is None else zero)
 
   # -- arithmetic --------------------------------------------------------------------
   def _coerce(self, other):
@@ -134,8 +143,10 @@ class Poly(object):
   def __mul__(self, other):
     other = self._coerce(other)
     out = {}
-    for p1, c1 in self._terms.items():
-      for p2, c2 in other._terms.items():
+    mine = [(k, thub(v, len(other._terms))) for k, v in self._terms.items()]      # Streams are used
+    theirs = [(k, thub(v, len(self._terms))) for k, v in other._terms.items()]    # once per partner term
+    for p1, c1 in mine:
+      for p2, c2 in theirs:
         p = p1 + p2
         if p in out:
           out[p] += c1 * c2
@@ -170,6 +181,7 @@ class Poly(object):
       if len(other) == 0:
         raise ZeroDivisionError("Dividing Poly instance by zero")
       raise NotImplementedError("Can't divide general Poly instances")
+    other = thub(other, len(self._terms))
     return Poly({k: operator.truediv(v, other) for k, v in self._terms.items()}, zero=self._zero)
 
   def diff(self, n=1):
@@ -211,13 +223,18 @@ class Poly(object):
   def __eq__(self, other):
     if not isinstance(other, Poly):
       other = Poly(other, zero=self._zero)
-    return self._zero == other._zero and self._terms == other._terms
+
+    def same(a, b):
+      return a is b if isinstance(a, Stream) or isinstance(b, Stream) else a == b
+
+    return same(self._zero, other._zero) and len(self._terms) == len(other._terms) and \
+      all(k in other._terms and same(v, other._terms[k]) for k, v in self._terms.items())
 
   def __ne__(self, other):
     return not (self == other)
 
   def __hash__(self):
-    return hash((frozenset(self._terms.items()), self._zero))
+    return hash((frozenset((k, id(v) if isinstance(v, Stream) else v) for k, v in self._terms.items()), self._zero))
 
   @property
   def roots(self):

@@ -67,7 +67,7 @@ typedef struct alz_plan_info {
   int32_t n_channels;        /* C: independent cascades fed by the same input stream  */
   int32_t n_sections;        /* K: sections per cascade after padding                 */
   int32_t num_taps;          /* NB template value (biquad kind) or max nb (generic)   */
-  int32_t monic;             /* 1 if b0 was factored out of every section             */
+  int32_t monic;             /* 0 plain; 1 b0 factored out, gain on the float64 output; 2 gain on the float32 input */
   int32_t state_doubles;     /* doubles of state per (stream, channel)                */
   int32_t fp64_ops;          /* FP64 instructions per channel-sample in the hot loop  */
   int32_t device;            /* CUDA device ordinal the plan lives on                 */
@@ -105,6 +105,12 @@ int32_t alz_set_device(int32_t device);
 int32_t alz_plan_create(const double* coef, const int32_t* section_desc,
                         int32_t n_channels, int32_t max_sections, alz_plan** out);
 
+/* Same with flags.  ALZ_PLAN_FORCE_GENERIC keeps every listed tap (also zero-valued ones are
+ * kept if non-zero in any channel) on the generic kernel: required for time-varying plans. */
+#define ALZ_PLAN_FORCE_GENERIC 1
+int32_t alz_plan_create_ex(const double* coef, const int32_t* section_desc, int32_t n_channels,
+                           int32_t max_sections, int32_t flags, alz_plan** out);
+
 void alz_plan_destroy(alz_plan* plan);
 
 int32_t alz_plan_info_get(const alz_plan* plan, alz_plan_info* out);
@@ -138,6 +144,19 @@ int32_t alz_plan_history(const alz_plan* plan, int32_t* xd, int32_t* yd);
 int32_t alz_apply_f32(const alz_plan* plan, const float* x_dev, float* y_dev,
                       double* state_dev, int64_t n_streams, int64_t n_samples,
                       int64_t x_stride, int64_t y_stride, void* cuda_stream);
+
+/*
+ * Time-varying coefficients (reference lazy_filters.py:200-216: Stream-valued b_k / a_k are
+ * advanced once per input sample).  For a single-channel GENERIC plan, alz_plan_taps() lists
+ * the taps in the order of the coefficient table: delay[i], is_den[i] (1 for feedback taps).
+ * alz_apply_tv_f32() filters a block with per-sample coefficients coef_dev[i * coef_stride + n]
+ * (device, float64): b_k[n] / a_0[n] for numerator taps, -a_k[n] / a_0[n] for feedback taps.
+ * All streams of the batch share the coefficient sequences.
+ */
+int32_t alz_plan_taps(const alz_plan* plan, int32_t* delay, int32_t* is_den, int32_t cap);
+int32_t alz_apply_tv_f32(const alz_plan* plan, const float* x_dev, float* y_dev, double* state_dev,
+                         int64_t n_streams, int64_t n_samples, int64_t x_stride, int64_t y_stride,
+                         const double* coef_dev, int64_t coef_stride, void* cuda_stream);
 
 /*
  * Same with HOST buffers: host->device copy of x, the kernel, device->host copy

@@ -143,6 +143,20 @@ def main():
   vectors["karplus_strong_y"] = np.array(ks.take(3000))
   vectors["accumulate_z_y"] = run(al.accumulate.z, signal(8, 500))
 
+  # ---------------------------------------------------------------- time-varying coefficients
+  xt = signal(9, 300)
+  St = al.Stream
+  tv = {
+    "tv_gain_delay": lambda: St(0.5, -1.0, 2.0) * al.z ** -2,
+    "tv_fir_div": lambda: (2 + St(1, 2, 3) * al.z ** -1) / St(1, 5),
+    "tv_a0": lambda: 1 / (St(1, 2, 3) - al.z ** -1),
+    "tv_iir": lambda: (0.5 + St(.3, -.2) * al.z ** -1) / (1 - St(.1, .7, -.5, -1e-3) * al.z ** -1 + 0.2 * al.z ** -2),
+  }
+  for key, make in tv.items():
+    vectors[key + "_y"] = run(make(), xt)
+  vectors["tv_iir_seeded_y"] = run(tv["tv_iir"](), xt, memory=[0.4, -0.3], zero=0.2)
+  vectors["tv_short_coef_y"] = run(al.Stream([1., 2., 3., 4., 5.]) * al.z ** -1 + 1, xt[:5])
+
   # ---------------------------------------------------------------- builders (designs only)
   grid = []
   for name in ["poles_exp", "freq_poles_exp", "z_exp", "freq_z_exp"]:

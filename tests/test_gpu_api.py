@@ -78,8 +78,6 @@ def test_identity_gain_delay_empty_lists(ab):
   assert list(mixed(data)) == [0.0, 3.0, -4.0, 0.5]
   with pytest.raises(ValueError, match="Non-causal"):
     (z + 1)(data)
-  with pytest.raises(NotImplementedError):
-    (1 + Stream(1, 2) * z ** -1)(data)
 
 
 def test_configs_through_the_python_api(ab, designs, vectors):
@@ -177,3 +175,34 @@ def test_callers_of_the_path(ab, vectors):
   ks = ab.karplus_strong(2 * np.pi * 220.5 / 44100, tau=5e3, memory=mem)      # endless silence in, seeded comb
   assert rel_err(ks.take(3000), vectors["karplus_strong_y"]) <= TOL
   assert rel_err(list(ab.accumulate_z(signal(8, 500).tolist())), vectors["accumulate_z_y"]) <= TOL
+
+
+def test_time_varying_coefficients(ab, vectors):
+  """SURVEY.md 8f item 4 / reference lazy_filters.py:169-176, 200-216: Stream-valued b_k, a_k, a_0;
+  golden outputs from the reference (tests/golden/make_golden.py)."""
+  z, St = ab.z, ab.Stream
+  xt = signal(9, 300).tolist()
+  filters = {
+    "tv_gain_delay": lambda: St(0.5, -1.0, 2.0) * z ** -2,
+    "tv_fir_div": lambda: (2 + St(1, 2, 3) * z ** -1) / St(1, 5),
+    "tv_a0": lambda: 1 / (St(1, 2, 3) - z ** -1),
+    "tv_iir": lambda: (0.5 + St(.3, -.2) * z ** -1) / (1 - St(.1, .7, -.5, -1e-3) * z ** -1 + 0.2 * z ** -2),
+  }
+  for key, make in filters.items():
+    filt = make()
+    assert not filt.is_lti()
+    out = filt(xt)
+    assert isinstance(out, St)
+    assert rel_err(list(out), vectors[key + "_y"]) <= TOL, key
+  assert rel_err(list(filters["tv_iir"]()(xt, memory=[0.4, -0.3], zero=0.2)), vectors["tv_iir_seeded_y"]) <= TOL
+  short = St([1., 2., 3., 4., 5.]) * z ** -1 + 1
+  assert rel_err(list(short(xt[:5])), vectors["tv_short_coef_y"]) <= TOL
+  # copies keep both filters usable (reference tests/test_filters.py::test_copy)
+  f1 = (2 + St(1, 2, 3) * z ** -1) / St(1, 5)
+  f2 = f1.copy()
+  assert list(f1(xt[:40])) == list(f2(xt[:40]))
+  # a long lazy input crosses several pump blocks
+  gain = St(1.0, 0.5)
+  out = (gain * z ** -1)(St(xt * 20)).take(3000)
+  want = [0.0] + [(1.0 if i % 2 == 0 else 0.5) * (xt * 20)[i - 1] for i in range(1, 3000)]
+  assert np.allclose(out, want, rtol=1e-6, atol=1e-7)
