@@ -193,7 +193,8 @@ class Plan(object):
     if y is None:
       y = np.empty((S, self.n_channels, T), dtype=np.float32)
     assert y.dtype == np.float32 and y.shape == (S, self.n_channels, T) and y.flags.c_contiguous
-    _check(lib().alz_apply_f32_host(self._h, x.ctypes.data, y.ctypes.data, state_ptr, S, T, x.strides[0] // 4, T))
+    x_stride = x.strides[0] // 4 if S > 1 else max(T, 1)   # a length-1 axis may carry any stride
+    _check(lib().alz_apply_f32_host(self._h, x.ctypes.data, y.ctypes.data, state_ptr, S, T, x_stride, T))
     return y
 
 

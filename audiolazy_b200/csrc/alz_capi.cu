@@ -133,7 +133,8 @@ static bool make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMa
   alz_encode_tiled_fn enc = get_encode_tiled();
   if (!enc || !ta.vec_in || !ta.vec_out || env_int("ALZ_NO_TMA", 0)) return false;
   if (ta.T >= (1ll << 31) || ta.S >= (1ll << 31)) return false;
-  if ((unsigned long long)ta.xs * 4 >= (1ull << 40) || (unsigned long long)ta.ys * 4 * ta.C >= (1ull << 40)) return false;
+  if ((unsigned long long)ta.xs * 4 >= (1ull << 40) || (unsigned long long)ta.ysS * 4 >= (1ull << 40)) return false;
+  if (ta.ysS & 3) return false;
   const cuuint32_t estr[3] = {1, 1, 1};
   {
     const cuuint64_t dims[2] = {(cuuint64_t)ta.T, (cuuint64_t)ta.S};
@@ -145,7 +146,7 @@ static bool make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMa
   }
   {
     const cuuint64_t dims[3] = {(cuuint64_t)ta.T, (cuuint64_t)ta.C, (cuuint64_t)ta.S};
-    const cuuint64_t strides[2] = {(cuuint64_t)ta.ys * 4, (cuuint64_t)ta.ys * 4 * ta.C};
+    const cuuint64_t strides[2] = {(cuuint64_t)ta.ys * 4, (cuuint64_t)ta.ysS * 4};
     const cuuint32_t box[3] = {32, 1, 32};
     if (enc(tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ta.y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -582,11 +583,144 @@ int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double
   return ALZ_OK;
 }
 
+static int apply_launch(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, cudaStream_t st,
+                        const double* tv, long long tv_stride) {
+  return p->kind == ALZ_KIND_BIQUAD ? launch_biquad(p, ta, state, sstride, st)
+                                    : launch_generic(p, ta, state, sstride, st, tv, tv_stride);
+}
+
+// ---- time-parallel evaluation of FEW long streams ------------------------------------------
+// A recurrence is serial in time, so one stream keeps one lane busy.  For an LTI filter the
+// state after a chunk is an affine function of the state before it:  s' = F + M s, where F is
+// the chunk's zero-state final state and M = A^L depends only on the coefficients.  So:
+//   pass 1  every chunk of L samples is filtered from a ZERO state, all chunks in parallel (a
+//           chunk is a "virtual stream": same kernels, x row stride L)         -> F_p
+//   basis   L zero samples from each unit state                                   -> M (d x d per channel)
+//   scan    s_{p+1} = F_p + M s_p, sequential over the P chunks (tiny kernel)     -> every chunk's true initial state
+//   pass 2  every chunk again, from its true initial state                        -> the output
+// Exact in exact arithmetic; in float64 the chunk states differ from the sequential ones by
+// rounding only (parity bar 1e-5; tests/test_gpu_parity.py::test_time_parallel_path).
+__global__ void alz_unit_state_kernel(double* m, int d, int C) {   // m[slot j][(i*C + c)] = (i == j)
+  const long long n = (long long)d * d * C;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long j = i / ((long long)d * C), rest = i - j * d * C;
+  m[i] = (rest / C == j) ? 1.0 : 0.0;
+}
+
+// One WARP per channel (d <= 32): lane j owns state slot j, keeps row j of M in registers and
+// the running state is exchanged with shuffles; F of the next chunk is prefetched.
+__global__ void __launch_bounds__(32) alz_chunk_scan_kernel(const double* __restrict__ F, double* __restrict__ init,
+                                                            const double* __restrict__ M, double* user_state,
+                                                            long long user_stride, int d, int C, long long P) {
+  const int c = blockIdx.x, j = threadIdx.x;
+  const bool on = j < d;
+  double mrow[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mrow[i] = (on && i < d) ? M[(long long)j * d * C + (long long)i * C + c] : 0.0;
+  double cur = on ? user_state[(long long)j * user_stride + c] : 0.0;
+  const long long pc = P * C;
+  const double* Fj = F + (long long)(on ? j : 0) * pc + c;
+  double* Ij = init + (long long)(on ? j : 0) * pc + c;
+  double f_next = (on && P > 0) ? Fj[0] : 0.0;
+  for (long long p = 0; p < P; ++p) {
+    const double f = f_next;
+    if (on) {
+      Ij[p * C] = cur;
+      if (p + 1 < P) f_next = Fj[(p + 1) * C];
+    }
+    double a0 = f, a1 = 0.0;                       // two partial sums: shorter dependency chain
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      a0 = fma(mrow[i], __shfl_sync(0xffffffffu, cur, i), a0);
+      a1 = fma(mrow[i + 1], __shfl_sync(0xffffffffu, cur, i + 1), a1);
+    }
+    cur = a0 + a1;
+  }
+  if (on) user_state[(long long)j * user_stride + c] = cur;
+}
+
+static bool chunked_applies(const alz_plan* p, long long S, long long T) {
+  if (p->kind != ALZ_KIND_BIQUAD || env_int("ALZ_NO_TIME_PARALLEL", 0)) return false;
+  if (S > 8 || T < 65536) return false;
+  return (long long)p->C * ((S + 31) / 32) <= 256 && p->state_doubles <= 32;
+}
+
+static int apply_chunked(const alz_plan* p, const float* x, float* y, double* state, long long sstride, long long S,
+                         long long T, long long xs, long long ys, cudaStream_t st) {
+  const int C = p->C, d = p->state_doubles;
+  // chunk count: enough virtual streams to give every SM sub-partition a few warps, at most
+  // 1024 (the scan over chunks is serial: ~200 cycles per chunk)
+  long long want = 2ll * 148 * 4 * 32 / C;
+  if (want > 1024) want = 1024;
+  if (want < 256) want = 256;
+  long long L = (T / want + 31) / 32 * 32;
+  if (L < 256) L = 256;
+  const long long P = T / L, Tmain = P * L;
+  const size_t nstate = (size_t)d * P * C;
+  {   // keep the stream-ordered pool's memory across calls (its default trims at every sync)
+    static std::once_flag once[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::call_once(once[dev & 63], [dev] {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    });
+  }
+  double *Z1 = nullptr, *Z2 = nullptr, *M = nullptr;
+  float *xz = nullptr, *ydum = nullptr;
+  ALZ_CUDA(cudaMallocAsync((void**)&Z1, nstate * 8, st));
+  ALZ_CUDA(cudaMallocAsync((void**)&Z2, nstate * 8, st));
+  ALZ_CUDA(cudaMallocAsync((void**)&M, (size_t)d * d * C * 8, st));
+  ALZ_CUDA(cudaMallocAsync((void**)&xz, (size_t)d * L * 4, st));
+  ALZ_CUDA(cudaMallocAsync((void**)&ydum, (size_t)d * C * L * 4, st));
+  ALZ_CUDA(cudaMemsetAsync(xz, 0, (size_t)d * L * 4, st));
+  int rc = ALZ_OK;
+  {   // basis run (once: M does not depend on the stream)
+    const long long n = (long long)d * d * C;
+    alz_unit_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(M, d, C);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    AlzTileArgs tb{};
+    tb.x = xz; tb.y = ydum; tb.S = d; tb.T = L; tb.xs = L; tb.ys = L; tb.ysS = (long long)C * L; tb.C = C;
+    tb.vec_in = tb.vec_out = 1;
+    rc = apply_launch(p, tb, M, (long long)d * C, st, nullptr, 0);
+  }
+  for (long long s = 0; s < S && rc == ALZ_OK; ++s) {
+    AlzTileArgs ta{};
+    ta.x = x + s * xs; ta.y = y + s * C * ys; ta.S = P; ta.T = L; ta.xs = L; ta.ys = ys; ta.ysS = L; ta.C = C;
+    ta.vec_in = (((uintptr_t)ta.x & 15) == 0) ? 1 : 0;
+    ta.vec_out = (((uintptr_t)ta.y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
+    ALZ_CUDA(cudaMemsetAsync(Z1, 0, nstate * 8, st));
+    rc = apply_launch(p, ta, Z1, P * C, st, nullptr, 0);                       // pass 1: zero-state chunks
+    if (rc != ALZ_OK) break;
+    alz_chunk_scan_kernel<<<C, 32, 0, st>>>(Z1, Z2, M, state + s * C, sstride, d, C, P);
+    ALZ_CUDA(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    rc = apply_launch(p, ta, Z2, P * C, st, nullptr, 0);                       // pass 2: true initial states
+    if (rc != ALZ_OK) break;
+    if (T > Tmain) {                                                           // ragged tail, sequentially
+      AlzTileArgs tt{};
+      tt.x = x + s * xs + Tmain; tt.y = y + s * C * ys + Tmain; tt.S = 1; tt.T = T - Tmain; tt.xs = xs; tt.ys = ys;
+      tt.ysS = (long long)C * ys; tt.C = C;
+      tt.vec_in = (((uintptr_t)tt.x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
+      tt.vec_out = (((uintptr_t)tt.y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
+      rc = apply_launch(p, tt, state + s * C, sstride, st, nullptr, 0);
+    }
+  }
+  cudaFreeAsync(Z1, st); cudaFreeAsync(Z2, st); cudaFreeAsync(M, st); cudaFreeAsync(xz, st); cudaFreeAsync(ydum, st);
+  return rc;
+}
+
 static int apply_impl(const alz_plan* p, const float* x, float* y, double* state, long long sstride, long long S,
                       long long T, long long xs, long long ys, cudaStream_t st, const double* tv = nullptr,
                       long long tv_stride = 0) {
+  if (!tv && chunked_applies(p, S, T)) return apply_chunked(p, x, y, state, sstride, S, T, xs, ys, st);
   AlzTileArgs ta{};
-  ta.T = T; ta.xs = xs; ta.ys = ys; ta.C = p->C; ta.c_base = 0;
+  ta.T = T; ta.xs = xs; ta.ys = ys; ta.ysS = (long long)p->C * ys; ta.C = p->C; ta.c_base = 0;
   ta.vec_in = (((uintptr_t)x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
   ta.vec_out = (((uintptr_t)y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
   const long long kMaxStreams = 65535ll * 32;   // gridDim.y limit
@@ -595,8 +729,7 @@ static int apply_impl(const alz_plan* p, const float* x, float* y, double* state
     ta.x = x + s0 * xs;
     ta.y = y + s0 * p->C * ys;
     double* stp = state + s0 * p->C;
-    const int rc = p->kind == ALZ_KIND_BIQUAD ? launch_biquad(p, ta, stp, sstride, st)
-                                               : launch_generic(p, ta, stp, sstride, st, tv, tv_stride);
+    const int rc = apply_launch(p, ta, stp, sstride, st, tv, tv_stride);
     if (rc != ALZ_OK) return rc;
   }
   return ALZ_OK;

@@ -41,6 +41,7 @@ struct AlzTileArgs {
   const float* x;   // [S] rows, stride xs
   float* y;         // [S*C] rows (stream-major, channel-minor), stride ys
   long long S, T, xs, ys;
+  long long ysS;    // y stride between consecutive STREAMS (C*ys for the dense [S][C][T] layout)
   int C;            // channels of the whole bank (row index = s*C + c)
   int c_base;       // first channel handled by this launch (blockIdx.x + c_base = c)
   int vec_in;       // 1: x rows are 16-byte aligned (16 B cp.async), 0: 4 B cp.async
@@ -124,7 +125,7 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
   const bool lean_out = a.vec_out && full_group;
   const int sub = lane >> 3, col = (lane & 7) << 2;
   float* const myrow0 = smem + lane * ALZ_PITCH;
-  const long long ystep = 4ll * a.C * a.ys;
+  const long long ystep = 4ll * a.ysS;
 
   // prologue: tiles 0 and 1 in flight
   alz_issue_tile(a, smem, s0, 0, lane, lean_in && nfull > 0);
@@ -142,7 +143,7 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
     __syncwarp();
 
     if (lean_out && i < nfull) {
-      float* dst = a.y + ((s0 + sub) * a.C + c) * a.ys + t0 + col;
+      float* dst = a.y + (s0 + sub) * a.ysS + c * a.ys + t0 + col;
       const float* src = buf + sub * ALZ_PITCH + col;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -156,7 +157,7 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
         const int row = it * 4 + sub;
         if (s0 + row < a.S && col < nvalid) {
           const float4 v = *reinterpret_cast<const float4*>(buf + row * ALZ_PITCH + col);
-          float* dst = a.y + ((s0 + row) * a.C + c) * a.ys + t0 + col;
+          float* dst = a.y + (s0 + row) * a.ysS + c * a.ys + t0 + col;
           if (a.vec_out && col + 4 <= nvalid) {
             alz_st_v4(dst, v);
           } else {

@@ -191,6 +191,24 @@ class LinearFilter(LinearFilterProperties):
     xinit, yinit = _seed_histories(sections, memory, zero)
     return _engine.filter_stream([sections], seq, [xinit], [yinit])
 
+  # -- batch API (no reference counterpart: arrays in, arrays out, no per-sample Python) ---
+  def as_bank(self):
+    """This filter as a one-channel :class:`~audiolazy_b200.bank.FilterBank`."""
+    from .bank import FilterBank
+    return FilterBank([self])
+
+  def apply(self, x, state=None):
+    """CUDA float32 tensor ``x[S, T]`` (or ``[T]``) -> tensor ``[S, T]``: S independent streams."""
+    y = self.as_bank().apply(x, state=state)
+    return y[:, 0] if x.dim() == 2 else y[0, 0]
+
+  def apply_host(self, x):
+    """float32 ndarray ``x[S, T]`` (or ``[T]``) on the host -> ndarray of the same shape."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float32)
+    y = self.as_bank().apply_host(x)
+    return y[:, 0] if x.ndim == 2 else y[0, 0]
+
   # -- analysis ----------------------------------------------------------------------
   @elementwise("freq", 1)
   def freq_response(self, freq):
@@ -436,6 +454,14 @@ class CascadeFilter(FilterList):
       xinit, yinit = _seed_histories(sections, kwargs.get("memory"), kwargs.get("zero", 0.))
       return _engine.filter_stream([sections], args[0], [xinit], [yinit])
     return reduce(lambda data, filt: filt(data, *args[1:], **kwargs), self.callables, args[0])
+
+  # batch API, as LinearFilter.apply / apply_host
+  def as_bank(self):
+    from .bank import FilterBank
+    return FilterBank([self])
+
+  apply = LinearFilter.apply
+  apply_host = LinearFilter.apply_host
 
   @property
   def numpoly(self):

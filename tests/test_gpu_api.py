@@ -206,3 +206,16 @@ def test_time_varying_coefficients(ab, vectors):
   out = (gain * z ** -1)(St(xt * 20)).take(3000)
   want = [0.0] + [(1.0 if i % 2 == 0 else 0.5) * (xt * 20)[i - 1] for i in range(1, 3000)]
   assert np.allclose(out, want, rtol=1e-6, atol=1e-7)
+
+
+def test_array_api_of_single_filters(ab, designs, vectors):
+  import torch
+  casc = ab.CascadeFilter([ab.ZFilter(r[:3], r[3:]) for r in designs["cfg2_sos"]])
+  x = signal(2, 50000)
+  y = casc.apply_host(x)
+  assert y.shape == (50000,) and rel_err(y, vectors["cfg2_y"]) <= TOL
+  xs = np.stack([x[:4000], signal(3, 4000)])
+  yt = casc.apply(torch.from_numpy(xs).cuda())
+  assert yt.shape == (2, 4000) and rel_err(yt[0].cpu().numpy(), vectors["cfg2_y"][:4000]) <= TOL
+  f = ab.ZFilter([1, 7, 2], [1, 0.5, 0.2])
+  assert rel_err(f.apply_host(signal(1, 48000)), vectors["cfg1_y"]) <= TOL

@@ -212,3 +212,23 @@ def test_full_size_properties(gpu, designs):
   torch.cuda.synchronize()
   assert torch.equal(y, y2)
   assert bool(torch.isfinite(y[::97]).all())
+
+
+def test_time_parallel_path(gpu, designs, monkeypatch):
+  """Few long streams (BASELINE configs 2 and 3) take the chunked zero-state / scan / replay
+  path; it must agree with the sequential path and the oracle, honour seeds and carry state."""
+  x = np.stack([signal(70 + i, 200000 + 77) for i in range(3)])
+  for bank, xi, yi in [(designs["bank_slaney"][:64], None, None),
+                       ([[(r[:3], r[3:]) for r in designs["cfg2_sos"]]], np.full((1, 4, 2), 0.25), np.full((1, 4, 2), -0.5)),
+                       (designs["bank_sampled"][:5], None, None)]:
+    plan = gpu.capi.Plan(bank)
+    fast = gpu.run(plan, x, xinit=xi, yinit=yi)
+    monkeypatch.setenv("ALZ_NO_TIME_PARALLEL", "1")
+    slow = gpu.run(plan, x, xinit=xi, yinit=yi)
+    monkeypatch.delenv("ALZ_NO_TIME_PARALLEL")
+    assert rel_err(fast, slow) <= 3e-6          # rounding of the chunk states only (sampled: ill-conditioned head FIR)
+    want = oracle.bank_apply(x[:1, :150000], bank, xinit=xi, yinit=yi)
+    assert rel_err(fast[:1, :, :150000], want) <= TOL
+    # state carry: a long block (chunked) followed by short ones (sequential) == one shot
+    split = gpu.run(plan, x, xinit=xi, yinit=yi, splits=[131072 + 5, 1000, 200077 - 131077 - 1000])
+    assert rel_err(split, fast) <= 3e-6
