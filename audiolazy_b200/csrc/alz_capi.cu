@@ -790,9 +790,16 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
   ALZ_CUDA(cudaSetDevice(p->device));
   HostPipe& hp = p->pipe;
   const long long C = p->C;
-  const long long Tp = (T + 3) & ~3LL;   // device row pitch: keeps every row 16-byte aligned
-  // chunk over streams: <= 128 MiB of output per chunk, at least 1 stream
-  long long Sc = (128LL << 20) / (C * Tp * 4);
+  const long long kChunkBytes = 128LL << 20;   // <= 128 MiB of output per staged chunk
+  // a chunk is (streams [s0, s0+Sc)) x (samples [t0, t0+Tc)): whole streams when they are short,
+  // time segments of one stream (state carried on the device) when a single stream is long
+  long long Tc = T;
+  if (C * ((T + 3) & ~3LL) * 4 > kChunkBytes) {
+    Tc = (kChunkBytes / (C * 4)) & ~31LL;
+    if (Tc < 32) Tc = 32;
+  }
+  const long long Tp = (Tc + 3) & ~3LL;         // device row pitch: keeps every row 16-byte aligned
+  long long Sc = kChunkBytes / (C * Tp * 4);
   if (Sc < 1) Sc = 1;
   if (Sc > S) Sc = S;
   const size_t need_x = (size_t)Sc * Tp * 4, need_y = (size_t)Sc * C * Tp * 4;
@@ -824,16 +831,26 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
   }
   int rc = ALZ_OK;
   int i = 0;
-  for (long long s0 = 0; s0 < S && rc == ALZ_OK; s0 += Sc, ++i) {
-    const int b = i % HostPipe::NBUF;
+  for (long long s0 = 0; s0 < S && rc == ALZ_OK; s0 += Sc) {
     const long long n = std::min<long long>(Sc, S - s0);
-    cudaStream_t st = hp.stream[b];
-    cudaError_t e = cudaMemcpy2DAsync(hp.dx[b], Tp * 4, xh + s0 * xs, xs * 4, T * 4, n, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
-    rc = apply_impl(p, hp.dx[b], hp.dy[b], st_buf + s0 * C, (long long)S * C, n, T, Tp, Tp, st);
-    if (rc != ALZ_OK) break;
-    e = cudaMemcpy2DAsync(yh + s0 * C * ys, ys * 4, hp.dy[b], Tp * 4, T * 4, n * C, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
+    cudaEvent_t prev = nullptr;   // time segments of the same streams must run in order (state dependency)
+    for (long long t0 = 0; t0 < T && rc == ALZ_OK; t0 += Tc, ++i) {
+      const long long nt = std::min<long long>(Tc, T - t0);
+      const int b = i % HostPipe::NBUF;
+      cudaStream_t st = hp.stream[b];
+      if (prev) { cudaStreamWaitEvent(st, prev, 0); cudaEventDestroy(prev); prev = nullptr; }
+      cudaError_t e = cudaMemcpy2DAsync(hp.dx[b], Tp * 4, xh + s0 * xs + t0, xs * 4, nt * 4, n, cudaMemcpyHostToDevice, st);
+      if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+      rc = apply_impl(p, hp.dx[b], hp.dy[b], st_buf + s0 * C, (long long)S * C, n, nt, Tp, Tp, st);
+      if (rc != ALZ_OK) break;
+      if (t0 + Tc < T) {
+        cudaEventCreateWithFlags(&prev, cudaEventDisableTiming);
+        cudaEventRecord(prev, st);
+      }
+      e = cudaMemcpy2DAsync(yh + s0 * C * ys + t0, ys * 4, hp.dy[b], Tp * 4, nt * 4, n * C, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
+    }
+    if (prev) cudaEventDestroy(prev);
   }
   for (int k = 0; k < HostPipe::NBUF; ++k) {
     cudaError_t e = cudaStreamSynchronize(hp.stream[k]);

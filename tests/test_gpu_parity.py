@@ -232,3 +232,30 @@ def test_time_parallel_path(gpu, designs, monkeypatch):
     # state carry: a long block (chunked) followed by short ones (sequential) == one shot
     split = gpu.run(plan, x, xinit=xi, yinit=yi, splits=[131072 + 5, 1000, 200077 - 131077 - 1000])
     assert rel_err(split, fast) <= 3e-6
+
+
+def test_host_path_time_segments(gpu, designs):
+  """A single long stream whose output exceeds one staging chunk is cut into time segments
+  (state carried on the device): same result as the device path."""
+  bank = designs["bank_slaney"]
+  plan = gpu.capi.Plan(bank)
+  x = signal(90, 600000)[None, :]                     # 64 ch x 600000 x 4 B = 154 MB > 128 MiB
+  want = gpu.run(plan, x)
+  got = plan.apply_host(x)
+  assert rel_err(got, want) <= 3e-6                    # time-parallel chunking differs between the two splits
+  assert rel_err(got[:, :, :20000], oracle.bank_apply(x[:, :20000], bank)) <= TOL
+
+
+def test_gain_modes(gpu, designs, monkeypatch):
+  """MONIC mode 2 (float32 input-side gain, default) and mode 1 (float64 output gain, ALZ_EXACT_GAIN=1)."""
+  bank = designs["bank_slaney"]
+  x = np.stack([signal(0, 8000), signal(7, 8000)])
+  want = oracle.bank_apply(x, bank)
+  fast = gpu.capi.Plan(bank)
+  assert fast.monic and fast.fp64_ops == 12
+  assert rel_err(gpu.run(fast, x), want) <= 2.5e-7
+  monkeypatch.setenv("ALZ_EXACT_GAIN", "1")
+  exact = gpu.capi.Plan(bank)
+  monkeypatch.delenv("ALZ_EXACT_GAIN")
+  assert exact.fp64_ops == 13
+  assert rel_err(gpu.run(exact, x), want) <= 6.5e-8   # = float32 rounding of the float64 result
