@@ -29,9 +29,10 @@
 //     in alz_state_init), so no rounding happens at block boundaries.
 //
 // Cost model (B200, measured): DFMA/DMUL with a uniform-register coefficient = 2.06
-// cycles per warp per SM sub-partition, F2F (either direction) ~4.  Slaney bank:
-// 13 x 2.06 + 2 x 4 = ~35 cycles per warp-sample: the kernel is FP64-issue bound below
-// the HBM roofline, by construction of the arithmetic the parity bar demands.
+// cycles per warp per SM sub-partition, F2F (either direction) ~3.85.  Slaney bank:
+// 12 x 2.06 + 2 x 3.85 = ~32.4 cycles per warp-sample (MONIC mode 2; 34.5 in mode 1): the
+// kernel is FP64-issue bound below the HBM roofline, by construction of the arithmetic the
+// parity bar demands.
 #pragma once
 #include "alz_lane.cuh"
 
