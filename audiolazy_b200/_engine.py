@@ -157,13 +157,12 @@ def filter_stream(bank_sections, seq, xinit, yinit, sum_channels=False):
   """Lazy Stream of a single-output filter call (one channel, or the channel sum)."""
   db = device_bank(bank_sections)   # errors (zero gain, no device) raise at call time, like the reference
 
-  def gen():
+  def rows():
     for block in _pump(db, seq, xinit, yinit, sum_channels):
-      row = block if sum_channels else block[0]
-      for value in row.tolist():
-        yield value
+      yield (block if sum_channels else block[0]).tolist()
 
-  return Stream(gen())
+  # chain.from_iterable walks the per-block lists in C: no Python frame per sample
+  return Stream(it.chain.from_iterable(rows()))
 
 
 def bank_streams(bank_sections, seq, xinit, yinit):
@@ -174,7 +173,7 @@ def bank_streams(bank_sections, seq, xinit, yinit):
   queues = [deque() for _ in range(C)]
   pump = _pump(db, seq, xinit, yinit, False)
 
-  def channel(c):
+  def channel(c):      # generator of per-block lists of channel c
     while True:
       while not queues[c]:
         try:
@@ -183,10 +182,9 @@ def bank_streams(bank_sections, seq, xinit, yinit):
           return
         for q, row in zip(queues, block):
           q.append(row.tolist())
-      for value in queues[c].popleft():
-        yield value
+      yield queues[c].popleft()
 
-  return [Stream(channel(c)) for c in range(C)]
+  return [Stream(it.chain.from_iterable(channel(c))) for c in range(C)]
 
 
 # --------------------------------------------------------------------------------------
@@ -248,9 +246,8 @@ def filter_stream_tv(num_terms, den_terms, seq, memory_init, zero):
       c_dev = torch.from_numpy(coef).to(device)
       y_dev = torch.empty(m, dtype=torch.float32, device=device)
       plan.apply_tv(x_dev.data_ptr(), y_dev.data_ptr(), state.data_ptr(), 1, m, m, m, c_dev.data_ptr(), m, cur())
-      for value in y_dev.cpu().numpy().tolist():
-        yield value
+      yield y_dev.cpu().numpy().tolist()
       if m < n:
         return
 
-  return Stream(gen())
+  return Stream(it.chain.from_iterable(gen()))
