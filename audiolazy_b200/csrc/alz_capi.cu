@@ -51,7 +51,7 @@ struct HostPipe {   // lazily created resources of alz_apply_f32_host
 };
 
 struct alz_plan {
-  int kind = 0, C = 0, K = 0, NB = 0, NB0 = 0, monic = 0, device = 0;
+  int kind = 0, C = 0, K = 0, NB = 0, NB0 = 0, monic = 0, device = 0, sm_count = 148;
   int xd = 0, yd = 0;          // history depths exposed to alz_state_init
   int state_doubles = 0;       // per recurrence
   int fp64_ops = 0;
@@ -72,6 +72,21 @@ struct alz_plan {
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
+}
+
+// Keep the stream-ordered pool's memory across calls (its default trims at every sync).
+static void keep_async_pool() {
+  static std::once_flag once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::call_once(once[dev & 63], [dev] {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  });
 }
 
 // Kernel-parameter coefficient capacity (doubles).  CUDA 12.1+ allows 32764 bytes of
@@ -170,7 +185,28 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
   const long long groups = (ta.S + 31) / 32;
   CUtensorMap tmx, tmy;
   if (make_tensor_maps(ta, &tmx, &tmy)) {
-    alz_biquad_tma_kernel<K, NB, MONIC, NCOEF, NB0><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
+    // A launch of only a few waves of warps loses its last, partly filled wave: cut time into
+    // segments chained through the state (alz_lane.cuh) so the next segment fills the tail.
+    const long long warps = (long long)nch * groups, slots = (long long)p->sm_count * kWarpsPerSmTma;
+    long long nseg = 1;
+    if (warps > slots && warps < 8 * slots && ta.T >= 2048 && !env_int("ALZ_NO_SEGMENT", 0)) {
+      const long long waves = env_int("ALZ_SEG_WAVES", 16), min_len = env_int("ALZ_SEG_MIN", 1024);
+      nseg = std::min((waves * slots + warps - 1) / warps, ta.T / min_len);
+      const long long len = ((ta.T + nseg - 1) / nseg + 31) / 32 * 32;
+      nseg = (ta.T + len - 1) / len;
+      if (nseg > 1 && groups * nseg <= 65535) {
+        const size_t words = (size_t)nch + (size_t)nch * groups;
+        unsigned* sync = nullptr;
+        keep_async_pool();
+        ALZ_CUDA(cudaMallocAsync(&sync, words * 4, st));
+        ALZ_CUDA(cudaMemsetAsync(sync, 0, words * 4, st));
+        ta.nseg = (int)nseg; ta.groups = (int)groups; ta.seg_len = len; ta.sync = sync;
+      } else {
+        nseg = 1;
+      }
+    }
+    alz_biquad_tma_kernel<K, NB, MONIC, NCOEF, NB0><<<dim3((unsigned)nch, (unsigned)(groups * nseg)), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
+    if (ta.sync) cudaFreeAsync(ta.sync, st);
   } else {
     alz_biquad_kernel<K, NB, MONIC, NCOEF, NB0><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
   }
@@ -317,6 +353,10 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
   if (!p) return fail(ALZ_ERR_NOMEM, "out of host memory");
   p->C = C;
   p->device = dev;
+  if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || p->sm_count <= 0) {
+    cudaGetLastError();
+    p->sm_count = 148;
+  }
 
   // numerator taps of the first section vs. of the later ones
   int nb_first = 1, nb_rest = 1;
@@ -519,12 +559,12 @@ int32_t alz_plan_history(const alz_plan* p, int32_t* xd, int32_t* yd) {
   return ALZ_OK;
 }
 
-// Broadcast one per-channel row of slot values to all streams: state[slot*R + s*C + c].
+// Broadcast one per-channel row of slot values to all streams: state[slot*R + c*S + s].
 __global__ void alz_state_fill_kernel(double* state, const double* proto, long long R, int C, int slots) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * slots) return;
-  const long long slot = i / R, r = i - slot * R;
-  state[i] = proto[slot * C + (int)(r % C)];
+  const long long slot = i / R, r = i - slot * R, S = R / C;
+  state[i] = proto[slot * C + (int)(r / S)];
 }
 
 int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double* xinit, const double* yinit,
@@ -600,34 +640,36 @@ static int apply_launch(const alz_plan* p, AlzTileArgs ta, double* state, long l
 //   pass 2  every chunk again, from its true initial state                        -> the output
 // Exact in exact arithmetic; in float64 the chunk states differ from the sequential ones by
 // rounding only (parity bar 1e-5; tests/test_gpu_parity.py::test_time_parallel_path).
-__global__ void alz_unit_state_kernel(double* m, int d, int C) {   // m[slot j][(i*C + c)] = (i == j)
+__global__ void alz_unit_state_kernel(double* m, int d, int C) {   // m[slot j][(c*d + i)] = (i == j)
   const long long n = (long long)d * d * C;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long j = i / ((long long)d * C), rest = i - j * d * C;
-  m[i] = (rest / C == j) ? 1.0 : 0.0;
+  m[i] = (rest % d == j) ? 1.0 : 0.0;
 }
 
 // One WARP per channel (d <= 32): lane j owns state slot j, keeps row j of M in registers and
 // the running state is exchanged with shuffles; F of the next chunk is prefetched.
 __global__ void __launch_bounds__(32) alz_chunk_scan_kernel(const double* __restrict__ F, double* __restrict__ init,
                                                             const double* __restrict__ M, double* user_state,
-                                                            long long user_stride, int d, int C, long long P) {
+                                                            long long user_stride, long long user_stot, int d, int C,
+                                                            long long P) {
   const int c = blockIdx.x, j = threadIdx.x;
   const bool on = j < d;
   double mrow[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) mrow[i] = (on && i < d) ? M[(long long)j * d * C + (long long)i * C + c] : 0.0;
-  double cur = on ? user_state[(long long)j * user_stride + c] : 0.0;
+  for (int i = 0; i < 32; ++i) mrow[i] = (on && i < d) ? M[(long long)j * d * C + (long long)c * d + i] : 0.0;
+  double* us = user_state + (long long)(on ? j : 0) * user_stride + (long long)c * user_stot;
+  double cur = on ? *us : 0.0;
   const long long pc = P * C;
-  const double* Fj = F + (long long)(on ? j : 0) * pc + c;
-  double* Ij = init + (long long)(on ? j : 0) * pc + c;
+  const double* Fj = F + (long long)(on ? j : 0) * pc + (long long)c * P;
+  double* Ij = init + (long long)(on ? j : 0) * pc + (long long)c * P;
   double f_next = (on && P > 0) ? Fj[0] : 0.0;
   for (long long p = 0; p < P; ++p) {
     const double f = f_next;
     if (on) {
-      Ij[p * C] = cur;
-      if (p + 1 < P) f_next = Fj[(p + 1) * C];
+      Ij[p] = cur;
+      if (p + 1 < P) f_next = Fj[p + 1];
     }
     double a0 = f, a1 = 0.0;                       // two partial sums: shorter dependency chain
 #pragma unroll
@@ -637,7 +679,7 @@ __global__ void __launch_bounds__(32) alz_chunk_scan_kernel(const double* __rest
     }
     cur = a0 + a1;
   }
-  if (on) user_state[(long long)j * user_stride + c] = cur;
+  if (on) *us = cur;
 }
 
 static bool chunked_applies(const alz_plan* p, long long S, long long T) {
@@ -658,19 +700,7 @@ static int apply_chunked(const alz_plan* p, const float* x, float* y, double* st
   if (L < 256) L = 256;
   const long long P = T / L, Tmain = P * L;
   const size_t nstate = (size_t)d * P * C;
-  {   // keep the stream-ordered pool's memory across calls (its default trims at every sync)
-    static std::once_flag once[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::call_once(once[dev & 63], [dev] {
-      cudaMemPool_t pool;
-      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-      }
-      cudaGetLastError();
-    });
-  }
+  keep_async_pool();
   double *Z1 = nullptr, *Z2 = nullptr, *M = nullptr;
   float *xz = nullptr, *ydum = nullptr;
   ALZ_CUDA(cudaMallocAsync((void**)&Z1, nstate * 8, st));
@@ -685,19 +715,19 @@ static int apply_chunked(const alz_plan* p, const float* x, float* y, double* st
     alz_unit_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(M, d, C);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     AlzTileArgs tb{};
-    tb.x = xz; tb.y = ydum; tb.S = d; tb.T = L; tb.xs = L; tb.ys = L; tb.ysS = (long long)C * L; tb.C = C;
+    tb.x = xz; tb.y = ydum; tb.S = d; tb.T = L; tb.xs = L; tb.ys = L; tb.ysS = (long long)C * L; tb.C = C; tb.Stot = d;
     tb.vec_in = tb.vec_out = 1;
     rc = apply_launch(p, tb, M, (long long)d * C, st, nullptr, 0);
   }
   for (long long s = 0; s < S && rc == ALZ_OK; ++s) {
     AlzTileArgs ta{};
-    ta.x = x + s * xs; ta.y = y + s * C * ys; ta.S = P; ta.T = L; ta.xs = L; ta.ys = ys; ta.ysS = L; ta.C = C;
+    ta.x = x + s * xs; ta.y = y + s * C * ys; ta.S = P; ta.T = L; ta.xs = L; ta.ys = ys; ta.ysS = L; ta.C = C; ta.Stot = P;
     ta.vec_in = (((uintptr_t)ta.x & 15) == 0) ? 1 : 0;
     ta.vec_out = (((uintptr_t)ta.y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
     ALZ_CUDA(cudaMemsetAsync(Z1, 0, nstate * 8, st));
     rc = apply_launch(p, ta, Z1, P * C, st, nullptr, 0);                       // pass 1: zero-state chunks
     if (rc != ALZ_OK) break;
-    alz_chunk_scan_kernel<<<C, 32, 0, st>>>(Z1, Z2, M, state + s * C, sstride, d, C, P);
+    alz_chunk_scan_kernel<<<C, 32, 0, st>>>(Z1, Z2, M, state + s, sstride, sstride / C, d, C, P);
     ALZ_CUDA(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
     rc = apply_launch(p, ta, Z2, P * C, st, nullptr, 0);                       // pass 2: true initial states
@@ -705,10 +735,10 @@ static int apply_chunked(const alz_plan* p, const float* x, float* y, double* st
     if (T > Tmain) {                                                           // ragged tail, sequentially
       AlzTileArgs tt{};
       tt.x = x + s * xs + Tmain; tt.y = y + s * C * ys + Tmain; tt.S = 1; tt.T = T - Tmain; tt.xs = xs; tt.ys = ys;
-      tt.ysS = (long long)C * ys; tt.C = C;
+      tt.ysS = (long long)C * ys; tt.C = C; tt.Stot = sstride / C;
       tt.vec_in = (((uintptr_t)tt.x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
       tt.vec_out = (((uintptr_t)tt.y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
-      rc = apply_launch(p, tt, state + s * C, sstride, st, nullptr, 0);
+      rc = apply_launch(p, tt, state + s, sstride, st, nullptr, 0);
     }
   }
   cudaFreeAsync(Z1, st); cudaFreeAsync(Z2, st); cudaFreeAsync(M, st); cudaFreeAsync(xz, st); cudaFreeAsync(ydum, st);
@@ -721,6 +751,7 @@ static int apply_impl(const alz_plan* p, const float* x, float* y, double* state
   if (!tv && chunked_applies(p, S, T)) return apply_chunked(p, x, y, state, sstride, S, T, xs, ys, st);
   AlzTileArgs ta{};
   ta.T = T; ta.xs = xs; ta.ys = ys; ta.ysS = (long long)p->C * ys; ta.C = p->C; ta.c_base = 0;
+  ta.Stot = sstride / p->C;
   ta.vec_in = (((uintptr_t)x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
   ta.vec_out = (((uintptr_t)y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
   const long long kMaxStreams = 65535ll * 32;   // gridDim.y limit
@@ -728,7 +759,7 @@ static int apply_impl(const alz_plan* p, const float* x, float* y, double* state
     ta.S = std::min(kMaxStreams, S - s0);
     ta.x = x + s0 * xs;
     ta.y = y + s0 * p->C * ys;
-    double* stp = state + s0 * p->C;
+    double* stp = state + s0;
     const int rc = apply_launch(p, ta, stp, sstride, st, tv, tv_stride);
     if (rc != ALZ_OK) return rc;
   }
@@ -841,7 +872,7 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
       if (prev) { cudaStreamWaitEvent(st, prev, 0); cudaEventDestroy(prev); prev = nullptr; }
       cudaError_t e = cudaMemcpy2DAsync(hp.dx[b], Tp * 4, xh + s0 * xs + t0, xs * 4, nt * 4, n, cudaMemcpyHostToDevice, st);
       if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
-      rc = apply_impl(p, hp.dx[b], hp.dy[b], st_buf + s0 * C, (long long)S * C, n, nt, Tp, Tp, st);
+      rc = apply_impl(p, hp.dx[b], hp.dy[b], st_buf + s0, (long long)S * C, n, nt, Tp, Tp, st);
       if (rc != ALZ_OK) break;
       if (t0 + Tc < T) {
         cudaEventCreateWithFlags(&prev, cudaEventDisableTiming);

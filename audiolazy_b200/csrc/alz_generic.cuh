@@ -11,7 +11,7 @@
 //
 // Histories live in global memory (the state buffer), one power-of-two ring per
 // section for the input and one for the output, indexed by the ABSOLUTE sample count
-// so that block splitting is bit-exact.  Layout state[slot * sstride + r], r = s*C + c.
+// so that block splitting is bit-exact.  Layout state[slot * sstride + r], r = c*Stot + s.
 // The tap structure (delays) is the union over channels, the coefficients are read
 // with warp-uniform addresses coef[tap * C + c] (all lanes of a warp share the channel).
 #pragma once

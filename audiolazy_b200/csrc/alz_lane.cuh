@@ -42,7 +42,16 @@ struct AlzTileArgs {
   float* y;         // [S*C] rows (stream-major, channel-minor), stride ys
   long long S, T, xs, ys;
   long long ysS;    // y stride between consecutive STREAMS (C*ys for the dense [S][C][T] layout)
-  int C;            // channels of the whole bank (row index = s*C + c)
+  long long Stot;   // streams the state buffer was sized for: recurrence index r = c * Stot + s
+  // Time segmentation (TMA engine only; nseg <= 1 = off).  The grid is (channels, groups*nseg);
+  // a CTA draws a ticket from its channel's counter, tickets map to (segment, group) segment-major,
+  // and segment k of a (channel, group) waits for the flag its segment k-1 raises after storing
+  // the state.  Fills the last partial wave of a launch with the next segment's work.
+  int nseg;
+  int groups;            // stream groups of this launch = ceil(S / 32)
+  long long seg_len;     // samples per segment (multiple of 32)
+  unsigned* sync;        // [channels of this launch] tickets, then [channels][groups] flags; zeroed per launch
+  int C;            // channels of the whole bank (output row index = s*C + c)
   int c_base;       // first channel handled by this launch (blockIdx.x + c_base = c)
   int vec_in;       // 1: x rows are 16-byte aligned (16 B cp.async), 0: 4 B cp.async
   int vec_out;      // 1: y rows are 16-byte aligned (st.v4), 0: scalar stores
@@ -99,7 +108,7 @@ __device__ __forceinline__ void alz_issue_tile(const AlzTileArgs& a, float* buf,
 
 // Core concept:
 //   struct Core {
-//     __device__ void load(const CoreArgs&, long long r /* = s*C + c */, int c_local, bool valid);
+//     __device__ void load(const CoreArgs&, long long r /* = c*Stot + s */, int c_local, bool valid);
 //     __device__ void tile(float* row, int swz, int nvalid, long long n_done);
 //         // row[0..nvalid) holds float32 inputs; overwrite them with float32 outputs.
 //         // n_done = samples already processed in this launch (warp-uniform).
@@ -113,7 +122,7 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
   const long long s0 = (long long)blockIdx.y * 32;
   const long long s = s0 + lane;
   const bool valid = s < a.S;
-  const long long r = (valid ? s : a.S - 1) * a.C + c;
+  const long long r = (long long)c * a.Stot + (valid ? s : a.S - 1);   // stream-fastest: coalesced state access
 
   Core core;
   core.load(ca, r, c_local, valid);

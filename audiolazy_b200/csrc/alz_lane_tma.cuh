@@ -57,10 +57,31 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   const int lane = threadIdx.x;
   const int c_local = blockIdx.x;              // CTA-uniform: coefficients go to uniform registers
   const int c = a.c_base + c_local;
-  const long long s0 = (long long)blockIdx.y * 32;
+  int group = blockIdx.y, seg = 0;
+  long long tbeg = 0, tlen = a.T;
+  unsigned* flag = nullptr;
+  if (a.nseg > 1) {
+    // Ticket order = start order within the channel, so the CTA that owns the previous segment
+    // of my (channel, group) is already running or done: the wait below cannot deadlock.
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(a.sync + c_local, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    seg = (int)(ticket / (unsigned)a.groups);
+    group = (int)(ticket - (unsigned)seg * (unsigned)a.groups);
+    tbeg = (long long)seg * a.seg_len;
+    tlen = a.T - tbeg < a.seg_len ? a.T - tbeg : a.seg_len;
+    flag = a.sync + gridDim.x + (size_t)c_local * a.groups + group;
+    if (seg > 0) {
+      unsigned done;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(done) : "l"(flag) : "memory");
+      } while (done < (unsigned)seg);
+    }
+  }
+  const long long s0 = (long long)group * 32;
   const long long s = s0 + lane;
   const bool valid = s < a.S;
-  const long long r = (valid ? s : a.S - 1) * a.C + c;
+  const long long r = (long long)c * a.Stot + (valid ? s : a.S - 1);   // stream-fastest: coalesced state access
 
   const unsigned tile0 = alz_smem_u32(smem);
   const unsigned mbar0 = tile0 + 2 * ALZ_TMA_TILE_BYTES;
@@ -74,14 +95,15 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   Core core;
   core.load(ca, r, c_local, valid);
 
-  const int ntiles = (int)((a.T + ALZ_TT - 1) / ALZ_TT);
-  const int nfull = (int)(a.T / ALZ_TT);
+  const int ntiles = (int)((tlen + ALZ_TT - 1) / ALZ_TT);
+  const int nfull = (int)(tlen / ALZ_TT);
+  const int tb = (int)tbeg;
   const int swz = lane & 7;
   float* const myrow = reinterpret_cast<float*>(smem) + lane * 32;
 
   if (lane == 0) {   // tile 0 in flight
     alz_mbar_expect_tx(mbar0, ALZ_TMA_TILE_BYTES);
-    alz_tma_load_2d(tile0, tmx, 0, (int)s0, mbar0);
+    alz_tma_load_2d(tile0, tmx, tb, (int)s0, mbar0);
   }
 
   for (int i = 0; i < ntiles; ++i) {
@@ -93,18 +115,23 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
       // whole barrier-wait ago, so this normally does not block).
       if (i >= 1) alz_bulk_wait_read0();
       alz_mbar_expect_tx(mbar0 + 8 * (b ^ 1), ALZ_TMA_TILE_BYTES);
-      alz_tma_load_2d(tile0 + (b ^ 1) * ALZ_TMA_TILE_BYTES, tmx, t0 + ALZ_TT, (int)s0, mbar0 + 8 * (b ^ 1));
+      alz_tma_load_2d(tile0 + (b ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, (int)s0, mbar0 + 8 * (b ^ 1));
     }
     alz_mbar_wait(mbar0 + 8 * b, (i >> 1) & 1);     // tile i has landed (async proxy writes visible after the wait)
-    const int nvalid = i < nfull ? ALZ_TT : (int)(a.T - t0);
+    const int nvalid = i < nfull ? ALZ_TT : (int)(tlen - t0);
     core.tile(myrow + b * (ALZ_TMA_TILE_BYTES / 4), swz, nvalid, t0);
     alz_fence_async_smem();                          // my generic-proxy writes -> visible to the TMA store
     __syncwarp();
     if (lane == 0) {
-      alz_tma_store_3d(tmy, t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
+      alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
       alz_bulk_commit();
     }
   }
   if (lane == 0) alz_bulk_wait0();                   // all output tiles are globally written before exit
-  if (valid) core.store(ca, r, a.T);
+  if (valid) core.store(ca, r, tlen);
+  if (flag != nullptr && seg + 1 < a.nseg) {         // hand the state to the next segment
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(flag), "r"((unsigned)(seg + 1)) : "memory");
+  }
 }

@@ -184,9 +184,10 @@ def test_error_codes(gpu):
   assert np.array_equal(y[0, 0], x) and np.array_equal(y[0, 1], x)
 
 
-def test_full_size_properties(gpu, designs):
+def test_full_size_properties(gpu, designs, monkeypatch):
   """BASELINE cfg 4 (64 ch x 4096 streams x 16384 samples), where the oracle cannot go:
-  stream independence, block-split exactness and spot rows against the oracle."""
+  stream independence, block-split exactness, time-segmented == unsegmented launch, and spot
+  rows against the oracle."""
   torch = gpu.torch
   bank = designs["bank_slaney"]
   plan = gpu.capi.Plan(bank)
@@ -212,6 +213,15 @@ def test_full_size_properties(gpu, designs):
   torch.cuda.synchronize()
   assert torch.equal(y, y2)
   assert bool(torch.isfinite(y[::97]).all())
+  # the launches above were time-segmented (8192 warps = 2.3 waves); one plain launch must agree bit for bit
+  monkeypatch.setenv("ALZ_NO_SEGMENT", "1")
+  y2.fill_(float("nan"))
+  st2 = torch.zeros_like(st)
+  plan.apply(x.data_ptr(), y2.data_ptr(), st2.data_ptr(), S, T, T, T, cur)
+  torch.cuda.synchronize()
+  monkeypatch.delenv("ALZ_NO_SEGMENT")
+  assert torch.equal(y, y2)
+  assert torch.equal(st, st2)
 
 
 def test_time_parallel_path(gpu, designs, monkeypatch):
