@@ -19,5 +19,7 @@ from .auditory import erb, gammatone, gammatone_erb_constants, erb_space, gammat
 from .bank import FilterBank, BankState
 from .callers import envelope, maverage, karplus_strong, accumulate_z, zeros, ones, impulse, white_noise
 from .io import chunks, WavStream, wav_batch, pcm_to_float32
+from .linear_prediction import (ParCorError, acorr, lag_matrix, toeplitz, levinson_durbin, lpc, parcor, parcor_stable,
+                                lsf, lsf_stable)
 
 __version__ = "0.1.0"

@@ -29,7 +29,7 @@ SYMBOLS = (
   "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_create_ex",
   "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32",
   "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
-  "alz_apply_f32_host", "alz_sum_channels_f32", "alz_launch_count",
+  "alz_apply_f32_host", "alz_sum_channels_f32", "alz_freq_response_f64", "alz_launch_count",
 )
 
 
@@ -91,6 +91,8 @@ def lib():
   L.alz_apply_f32_host.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64]
   L.alz_sum_channels_f32.restype = i32
   L.alz_sum_channels_f32.argtypes = [vp, vp, i64, i32, i64, i64, i64, vp]
+  L.alz_freq_response_f64.restype = i32
+  L.alz_freq_response_f64.argtypes = [vp, vp, vp, i64, vp]
   L.alz_launch_count.restype = i64
   _lib = L
   return L
@@ -177,6 +179,10 @@ class Plan(object):
     is_den = np.zeros(n, dtype=np.int32)
     _check(lib().alz_plan_taps(self._h, delay.ctypes.data, is_den.ctypes.data, n))
     return list(zip(delay.tolist(), [bool(v) for v in is_den.tolist()]))
+
+  def freq_response(self, w_ptr, out_ptr, n, stream=0):
+    """Bank response on a grid: ``out[C][n][2]`` float64 (re, im) for ``w[n]`` rad/sample (device pointers)."""
+    _check(lib().alz_freq_response_f64(self._h, w_ptr, out_ptr, int(n), stream))
 
   def apply_tv(self, x_ptr, y_ptr, state_ptr, n_streams, n_samples, x_stride, y_stride, coef_ptr, coef_stride, stream=0):
     _check(lib().alz_apply_tv_f32(self._h, x_ptr, y_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),

@@ -94,6 +94,15 @@ class DeviceBank(object):
                     T, torch.cuda.current_stream(x.device).cuda_stream)
     return out
 
+  def freq_response(self, freqs):
+    """Complex response of every channel on ``freqs`` (rad/sample; array-like or CUDA float64
+    tensor): CUDA complex128 tensor ``[C, n]`` (reference ``lazy_filters.py:267-301`` per filter)."""
+    torch = torch_mod()
+    w = torch.as_tensor(freqs, dtype=torch.float64).to(self.device).contiguous().reshape(-1)
+    out = torch.empty((self.n_channels, w.numel(), 2), dtype=torch.float64, device=self.device)
+    self.plan.freq_response(w.data_ptr(), out.data_ptr(), w.numel(), torch.cuda.current_stream(self.device).cuda_stream)
+    return torch.view_as_complex(out)
+
   def sum_channels(self, y):
     torch = torch_mod()
     S, C, T = y.shape

@@ -86,6 +86,12 @@ class FilterBank(list):
       raise ValueError("state was created for %d streams, x has %d" % (state.n_streams, x.shape[0]))
     return db.apply(x, state.tensor, out=out)
 
+  def freq_response(self, freqs):
+    """Complex128 ndarray ``[C, n]``: every channel's response on the grid ``freqs`` (rad/sample),
+    evaluated on the device (the per-filter ``freq_response`` of reference
+    ``lazy_filters.py:267-301``, batched over the bank)."""
+    return self.device_bank().freq_response(np.asarray(freqs, dtype=np.float64)).cpu().numpy()
+
   def apply_host(self, x, out=None, state=None):
     """``x``: float32 ndarray ``[S, T]`` (or ``[T]``) on the host; returns ndarray ``[S, C, T]``.
     Goes through ``alz_apply_f32_host`` (pipelined H2D / kernel / D2H)."""

@@ -65,6 +65,12 @@ struct alz_plan {
   std::vector<AlzGenSection> h_sec;       // generic
   std::vector<int> h_xlen, h_ylen;        // generic: true max delays per section
   std::vector<int> h_tap_delay, h_tap_is_den;   // generic: tap order of the coefficient table
+  // normalised sections as given (a0 == 1), for alz_freq_response_f64
+  std::vector<double> fr_coef;            // b then a of every (channel, section), concatenated
+  std::vector<int> fr_desc;               // [C][K][3] = nb, na, offset (nb == 0: absent)
+  double* d_fr_coef = nullptr;
+  int fr_K = 0;
+  int* d_fr_desc = nullptr;
   std::mutex host_mu;
   HostPipe pipe;
 };
@@ -358,6 +364,16 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
     p->sm_count = 148;
   }
 
+  p->fr_desc.assign((size_t)C * Kmax * 3, 0);
+  for (int c = 0; c < C; ++c)
+    for (size_t k = 0; k < secs[c].size(); ++k) {
+      int* d = &p->fr_desc[((size_t)c * Kmax + k) * 3];
+      d[0] = (int)secs[c][k].b.size(); d[1] = (int)secs[c][k].a.size(); d[2] = (int)p->fr_coef.size();
+      p->fr_coef.insert(p->fr_coef.end(), secs[c][k].b.begin(), secs[c][k].b.end());
+      p->fr_coef.insert(p->fr_coef.end(), secs[c][k].a.begin(), secs[c][k].a.end());
+    }
+  p->fr_K = Kmax;
+
   // numerator taps of the first section vs. of the later ones
   int nb_first = 1, nb_rest = 1;
   for (int c = 0; c < C; ++c)
@@ -527,6 +543,8 @@ void alz_plan_destroy(alz_plan* p) {
   cudaFree(p->d_coef);
   cudaFree(p->d_sec);
   cudaFree(p->d_tap_delay);
+  cudaFree(p->d_fr_coef);
+  cudaFree(p->d_fr_desc);
   cudaSetDevice(cur);
   cudaGetLastError();
   delete p;
@@ -684,7 +702,7 @@ __global__ void __launch_bounds__(32) alz_chunk_scan_kernel(const double* __rest
 
 static bool chunked_applies(const alz_plan* p, long long S, long long T) {
   if (p->kind != ALZ_KIND_BIQUAD || env_int("ALZ_NO_TIME_PARALLEL", 0)) return false;
-  if (S > 8 || T < 65536) return false;
+  if (S > 32 || T < 65536) return false;   // one warp row of streams: sequential would leave the machine ~2% occupied
   return (long long)p->C * ((S + 31) / 32) <= 256 && p->state_doubles <= 32;
 }
 
@@ -911,6 +929,68 @@ int32_t alz_sum_channels_f32(const float* y, float* out, int64_t S, int32_t C, i
   alz_sum_channels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(y, out, S, C, T, ys, os);
   ALZ_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ALZ_OK;
+}
+
+// H_c(e^{jw}) = prod_k B_ck(z^-1) / A_ck(z^-1) at z^-1 = e^{-jw}: one thread per (channel, frequency),
+// Horner in complex float64 (reference lazy_filters.py:267-301 evaluates numpoly / denpoly the same way).
+__global__ void alz_freq_response_kernel(const double* __restrict__ coef, const int* __restrict__ desc, int C, int K,
+                                         const double* __restrict__ w, long long n, double* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (i >= n) return;
+  double zi, zr;
+  sincos(-w[i], &zi, &zr);
+  double hr = 1.0, hi = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const int* d = desc + ((size_t)c * K + k) * 3;
+    if (d[0] == 0) break;
+    const double* b = coef + d[2];
+    const double* a = b + d[0];
+    double nr = b[d[0] - 1], ni = 0.0;
+    for (int j = d[0] - 2; j >= 0; --j) {
+      const double tr = nr * zr - ni * zi + b[j];
+      ni = nr * zi + ni * zr;
+      nr = tr;
+    }
+    double dr = a[d[1] - 1], di = 0.0;
+    for (int j = d[1] - 2; j >= 0; --j) {
+      const double tr = dr * zr - di * zi + a[j];
+      di = dr * zi + di * zr;
+      dr = tr;
+    }
+    const double den = dr * dr + di * di;      // 0 -> NaN, like the reference's nan for a pole on the grid
+    const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
+    const double tr = hr * qr - hi * qi;
+    hi = hr * qi + hi * qr;
+    hr = tr;
+  }
+  out[((size_t)c * n + i) * 2 + 0] = hr;
+  out[((size_t)c * n + i) * 2 + 1] = hi;
+}
+
+int32_t alz_freq_response_f64(alz_plan* p, const double* w, double* out, int64_t n, void* cuda_stream) {
+  if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (n < 0) return fail(ALZ_ERR_INVALID, "negative size");
+  if (n == 0) return ALZ_OK;
+  if (!w || !out) return fail(ALZ_ERR_INVALID, "null buffer");
+  int cur = -1;
+  ALZ_CUDA(cudaGetDevice(&cur));
+  if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
+  {
+    std::lock_guard<std::mutex> lock(p->host_mu);
+    if (!p->d_fr_desc) {
+      ALZ_CUDA(cudaMalloc(&p->d_fr_desc, p->fr_desc.size() * sizeof(int)));
+      ALZ_CUDA(cudaMalloc(&p->d_fr_coef, std::max<size_t>(1, p->fr_coef.size()) * sizeof(double)));
+      ALZ_CUDA(cudaMemcpy(p->d_fr_desc, p->fr_desc.data(), p->fr_desc.size() * sizeof(int), cudaMemcpyHostToDevice));
+      ALZ_CUDA(cudaMemcpy(p->d_fr_coef, p->fr_coef.data(), p->fr_coef.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
+  alz_freq_response_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)p->C), 128, 0, (cudaStream_t)cuda_stream>>>(
+      p->d_fr_coef, p->d_fr_desc, p->C, p->fr_K, w, n, out);
+  ALZ_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (cur != p->device) cudaSetDevice(cur);
   return ALZ_OK;
 }
 

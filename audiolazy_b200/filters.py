@@ -37,7 +37,8 @@ import operator
 from collections import OrderedDict
 from collections.abc import Iterable
 from functools import reduce
-from math import cos, exp, pi, sin, sqrt, inf, e, nan
+import math
+from math import pi, inf, e, nan
 from numbers import Real
 
 from .core import StrategyDict
@@ -544,7 +545,23 @@ class ParallelFilter(FilterList):
 
 # --------------------------------------------------------------------------------------
 # coefficient builders (float64 host arithmetic, same operation order as the reference)
+#
+# A design parameter may be a Stream (one value per sample): the math functions below map
+# over iterables, every intermediate that the formula reads more than once goes through
+# ``thub`` with its read count (a no-op for plain numbers), and the result is a ZFilter with
+# Stream coefficients, i.e. a time-varying filter (reference ``lazy_filters.py:1202-1206``,
+# ``examples/lptv.py:28-38``).
 # --------------------------------------------------------------------------------------
+cos, sin, exp, sqrt = (elementwise("x", 0)(f) for f in (math.cos, math.sin, math.exp, math.sqrt))
+
+
+def _unit_if_zero(values):
+  """``values`` with zeros replaced by one (number or Stream)."""
+  if isinstance(values, Iterable):
+    return Stream(v if v else 1 for v in values)
+  return values if values else 1
+
+
 comb = StrategyDict("comb")
 
 
@@ -573,8 +590,8 @@ resonator = StrategyDict("resonator")
 @resonator.strategy("poles_exp")
 def resonator(freq, bandwidth):
   """Two-pole resonator, 0 dB at ``freq``; ``R = exp(-bandwidth / 2)`` (ref ``:1179-1209``)."""
-  R = exp(-bandwidth * .5)
-  cost = cos(freq) * (2 * R) / (1 + R ** 2)
+  R = thub(exp(-bandwidth * .5), 5)
+  cost = thub(cos(freq) * (2 * R) / (1 + R ** 2), 2)
   gain = (1 - R ** 2) * sqrt(1 - cost ** 2)
   denominator = 1 - 2 * R * cost * z ** -1 + R ** 2 * z ** -2
   return gain / denominator
@@ -583,7 +600,8 @@ def resonator(freq, bandwidth):
 @resonator.strategy("freq_poles_exp")
 def resonator(freq, bandwidth):
   """Two-pole resonator whose ``freq`` is the pole angle (ref ``:1212-1242``)."""
-  R = exp(-bandwidth * .5)
+  R = thub(exp(-bandwidth * .5), 3)
+  freq = thub(freq, 2)
   gain = (1 - R ** 2) * sin(freq)
   denominator = 1 - 2 * R * cos(freq) * z ** -1 + R ** 2 * z ** -2
   return gain / denominator
@@ -592,7 +610,7 @@ def resonator(freq, bandwidth):
 @resonator.strategy("z_exp")
 def resonator(freq, bandwidth):
   """Two-pole resonator with zeros at DC and Nyquist, 0 dB at ``freq`` (ref ``:1245-1276``)."""
-  R = exp(-bandwidth * .5)
+  R = thub(exp(-bandwidth * .5), 5)
   cost = cos(freq) * (1 + R ** 2) / (2 * R)
   gain = (1 - R ** 2) * .5
   numerator = 1 - z ** -2
@@ -603,7 +621,7 @@ def resonator(freq, bandwidth):
 @resonator.strategy("freq_z_exp")
 def resonator(freq, bandwidth):
   """Like ``z_exp`` with ``freq`` as the pole angle (ref ``:1279-1310``)."""
-  R = exp(-bandwidth * .5)
+  R = thub(exp(-bandwidth * .5), 3)
   gain = (1 - R ** 2) * .5
   numerator = 1 - z ** -2
   denominator = 1 - 2 * R * cos(freq) * z ** -1 + R ** 2 * z ** -2
@@ -617,27 +635,26 @@ highpass = StrategyDict("highpass")
 @lowpass.strategy("pole")
 def lowpass(cutoff):
   """One-pole lowpass, -3.0103 dB at ``cutoff`` rad/sample, 0 dB at DC (ref ``:1370-1378``)."""
-  x = 2 - cos(cutoff)
-  R = x - sqrt(x ** 2 - 1)
+  x = thub(2 - cos(cutoff), 2)
+  R = thub(x - sqrt(x ** 2 - 1), 2)
   return (1 - R) / (1 - R * z ** -1)
 
 
 @highpass.strategy("pole")
 def highpass(cutoff):
   """One-pole highpass, 0 dB at Nyquist (ref ``:1381-1389``)."""
-  x = 2 + cos(cutoff)
-  R = x - sqrt(x ** 2 - 1)
+  x = thub(2 + cos(cutoff), 2)
+  R = thub(x - sqrt(x ** 2 - 1), 2)
   return (1 - R) / (1 + R * z ** -1)
 
 
 @lowpass.strategy("z")
 def lowpass(cutoff):
   """One-pole one-zero lowpass (ref ``:1392-1405``)."""
+  cutoff = thub(cutoff, 2)
   numR = sin(cutoff) - 1
-  denR = cos(cutoff)
-  if not denR:
-    denR = 1   # the numerator is already zero
-  R = numR / denR
+  denR = _unit_if_zero(cos(cutoff))   # where cos is zero the numerator is zero too
+  R = thub(numR / denR, 2)
   gain = (1 + R) / 2
   return gain * (1 + z ** -1) / (1 + R * z ** -1)
 
@@ -645,11 +662,10 @@ def lowpass(cutoff):
 @highpass.strategy("z")
 def highpass(cutoff):
   """One-pole one-zero highpass (ref ``:1408-1421``)."""
+  cutoff = thub(cutoff, 2)
   numR = 1 - sin(cutoff)
-  denR = cos(cutoff)
-  if not denR:
-    denR = 1
-  R = numR / denR
+  denR = _unit_if_zero(cos(cutoff))
+  R = thub(numR / denR, 2)
   gain = (1 + R) / 2
   return gain * (1 - z ** -1) / (1 - R * z ** -1)
 
@@ -657,21 +673,21 @@ def highpass(cutoff):
 @lowpass.strategy("pole_exp")
 def lowpass(cutoff):
   """Matched-Z one-pole lowpass, ``R = exp(-cutoff)`` (ref ``:1424-1437``)."""
-  R = exp(-cutoff)
+  R = thub(exp(-cutoff), 2)
   return (1 - R) / (1 - R * z ** -1)
 
 
 @highpass.strategy("pole_exp")
 def highpass(cutoff):
   """Matched-Z one-pole highpass, ``R = exp(cutoff - pi)`` (ref ``:1440-1454``)."""
-  R = exp(cutoff - pi)
+  R = thub(exp(cutoff - pi), 2)
   return (1 - R) / (1 + R * z ** -1)
 
 
 @lowpass.strategy("z_exp")
 def lowpass(cutoff):
   """Matched-Z one-pole one-zero lowpass, ``R = exp(cutoff - pi)`` (ref ``:1457-1472``)."""
-  R = exp(cutoff - pi)
+  R = thub(exp(cutoff - pi), 2)
   G = (R + 1) / 2
   return G * (1 + z ** -1) / (1 + R * z ** -1)
 
@@ -679,7 +695,7 @@ def lowpass(cutoff):
 @highpass.strategy("z_exp")
 def highpass(cutoff):
   """Matched-Z one-pole one-zero highpass, ``R = exp(-cutoff)`` (ref ``:1475-1490``)."""
-  R = exp(-cutoff)
+  R = thub(exp(-cutoff), 2)
   G = (R + 1) / 2
   return G * (1 - z ** -1) / (1 - R * z ** -1)
 

@@ -21,6 +21,9 @@
  *                           pump or any host caller uses); copies are inside.
  *   alz_sum_channels_f32 <- ParallelFilter.__call__'s left-associated
  *                           elementwise sum (lazy_filters.py:1048-1054).
+ *   alz_freq_response_f64 <- LinearFilter.freq_response / CascadeFilter.freq_response
+ *                           (lazy_filters.py:267-301, :1000-1003) for a whole bank
+ *                           on a frequency grid.
  *
  * Conventions: plain pointers and sizes only; no exceptions cross the ABI; every
  * function returns 0 on success or a negative alz_status; alz_last_error() gives a
@@ -180,6 +183,17 @@ int32_t alz_apply_f32_host(const alz_plan* plan, const float* x_host, float* y_h
 int32_t alz_sum_channels_f32(const float* y_dev, float* out_dev, int64_t n_streams,
                              int32_t n_channels, int64_t n_samples, int64_t y_stride,
                              int64_t out_stride, void* cuda_stream);
+
+/*
+ * Frequency response of every channel of the plan on a grid: out[c][i] =
+ * prod_k B_ck(e^{-j w[i]}) / A_ck(e^{-j w[i]}) as interleaved (re, im) float64,
+ * out_dev sized [n_channels][n][2]; w_dev in rad/sample.  A pole exactly on the
+ * grid gives NaN (reference lazy_filters.py:267-301 evaluates numpoly/denpoly at
+ * exp(-1j*freq); CascadeFilter multiplies the sections' responses, :1000-1003).
+ * Device buffers; asynchronous on `cuda_stream`.
+ */
+int32_t alz_freq_response_f64(alz_plan* plan, const double* w_dev, double* out_dev, int64_t n,
+                              void* cuda_stream);
 
 /* Number of kernel launches issued by this library since load (bench bookkeeping). */
 int64_t alz_launch_count(void);

@@ -89,6 +89,17 @@ def main():
       outs.append(run(al.gammatone[name](fcs[c] * Hz, bw), imp))
     vectors["bank_%s_impulse" % name] = np.stack(outs)
 
+  # frequency responses of the same channels (lazy_filters.py:267-301 via CascadeFilter, :1007)
+  grid = np.concatenate([np.linspace(0.0, np.pi, 193), 2 * np.pi * np.array(fcs)[bank_channels] / 48000.0])
+  vectors["freq_grid"] = grid
+  for name in ["slaney", "klapuri", "sampled"]:
+    rows = []
+    for c in bank_channels:
+      bw = al.gammatone_erb_constants(4)[0] * al.erb(fcs[c] * Hz, Hz)
+      filt = al.gammatone[name](fcs[c] * Hz, bw)
+      rows.append([complex(filt.freq_response(float(w))) for w in grid])
+    vectors["bank_%s_freq_response" % name] = np.array(rows, dtype=np.complex128)
+
   # ---------------------------------------------------------------- cfg 1
   x1 = signal(1, 48000)
   vectors["cfg1_y"] = run(al.ZFilter([1, 7, 2], [1, 0.5, 0.2]), x1)
@@ -156,6 +167,48 @@ def main():
     vectors[key + "_y"] = run(make(), xt)
   vectors["tv_iir_seeded_y"] = run(tv["tv_iir"](), xt, memory=[0.4, -0.3], zero=0.2)
   vectors["tv_short_coef_y"] = run(al.Stream([1., 2., 3., 4., 5.]) * al.z ** -1 + 1, xt[:5])
+
+  # Stream-valued DESIGN parameters (lazy_filters.py:1202-1206, examples/lptv.py:28-38): the builder
+  # returns a filter whose coefficients are Streams
+  sweep = lambda: al.Stream(0.1 + 0.001 * k for k in range(100000))
+  tvb = {
+    "tvb_resonator_poles_exp": lambda: al.resonator.poles_exp(sweep(), 0.05),
+    "tvb_resonator_z_exp_bw": lambda: al.resonator.z_exp(0.3, sweep() * 0.1),
+    "tvb_resonator_freq_z_exp_both": lambda: al.resonator.freq_z_exp(sweep(), sweep() * 0.1),
+    "tvb_lowpass_pole": lambda: al.lowpass.pole(sweep()),
+    "tvb_highpass_z": lambda: al.highpass.z(sweep()),
+    "tvb_comb_tau": lambda: al.comb.tau(7, sweep() * 100),
+  }
+  xb = signal(10, 2500)
+  for key, make in tvb.items():
+    vectors[key + "_y"] = run(make(), xb)
+    filt = make()
+    rows = [np.array(c.take(40) if hasattr(c, "take") else [c] * 40, dtype=np.float64)
+            for poly in (filt.numpoly, filt.denpoly) for _, c in poly.terms()]
+    vectors[key + "_coefs"] = np.stack(rows)
+
+  # ---------------------------------------------------------------- LPC (lazy_lpc.py) -- SURVEY 8f item 2
+  np.mat = np.asmatrix          # the reference's elementwise() still looks numpy.mat up (removed in NumPy 2)
+  rng = np.random.default_rng(5)
+  n = np.arange(240)
+  blk = (np.sin(0.3 * n) + 0.5 * np.sin(1.1 * n + 1) + 0.05 * rng.standard_normal(240)).astype(np.float32)
+  blk_list = blk.astype(np.float64).tolist()
+  lpc_cases = []
+  for name in ["autocor", "nautocor", "kautocor", "covar", "kcovar"]:
+    for order in [1, 2, 6, 14]:
+      filt = al.lpc[name](blk_list, order)
+      lpc_cases.append({"strategy": name, "order": order, "numerator": [float(c) for c in filt.numerator],
+                        "error": float(filt.error)})
+  filt8 = al.lpc.kautocor(blk_list, 8)
+  designs["lpc"] = {"cases": lpc_cases, "parcor8": [float(k) for k in al.parcor(filt8)],
+                    "lsf8": [float(w) for w in al.lsf(filt8)],
+                    "acorr9": [float(v) for v in al.acorr(blk_list, 9)],
+                    "lag_matrix3": [[float(v) for v in row] for row in al.lag_matrix(blk_list, 3)]}
+  vectors["lpc_blk"] = blk
+  filt12 = al.lpc.kautocor(blk_list, 12)
+  resid = run(filt12, blk)                                   # analysis (whitening) FIR of order 12
+  vectors["lpc_residual_y"] = resid
+  vectors["lpc_synth_y"] = run(1 / filt12, resid.astype(np.float32))   # all-pole synthesis from the float32 residual
 
   # ---------------------------------------------------------------- builders (designs only)
   grid = []

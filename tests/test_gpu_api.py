@@ -219,3 +219,40 @@ def test_array_api_of_single_filters(ab, designs, vectors):
   assert yt.shape == (2, 4000) and rel_err(yt[0].cpu().numpy(), vectors["cfg2_y"][:4000]) <= TOL
   f = ab.ZFilter([1, 7, 2], [1, 0.5, 0.2])
   assert rel_err(f.apply_host(signal(1, 48000)), vectors["cfg1_y"]) <= TOL
+
+
+def test_bank_freq_response_on_device(ab, vectors):
+  """FilterBank.freq_response (alz_freq_response_f64) against the reference's own
+  freq_response values (golden) and the host evaluation of the same filters."""
+  grid = vectors["freq_grid"]
+  chans = vectors["bank_channels"]
+  for name in ["slaney", "klapuri", "sampled"]:
+    bank = ab.gammatone_bank(strategy=name)
+    got = bank.freq_response(grid)
+    assert got.shape == (64, len(grid)) and got.dtype == np.complex128
+    want = vectors["bank_%s_freq_response" % name]
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    # Horner on normalised sections vs the reference's Poly evaluation: rounding only; the 8-tap
+    # numerator of "sampled" cancels heavily in the lowest channels (SURVEY 8c: 3.5e-8 vs lfilter)
+    tol = 5e-8 if name == "sampled" else 1e-10
+    assert (np.abs(got[chans] - want) / scale).max() <= tol
+    host = np.array([[complex(bank[c].freq_response(float(w))) for w in grid[::16]] for c in (0, 31, 63)])
+    assert (np.abs(got[[0, 31, 63]][:, ::16] - host) / np.abs(host).max(axis=1, keepdims=True)).max() <= tol
+  # unit gain at each channel's own centre frequency (the designs are normalised there)
+  peak = np.abs(ab.gammatone_bank(strategy="slaney").freq_response(grid[193:]))[chans, np.arange(len(chans))]
+  assert np.abs(peak - 1).max() <= 1e-9
+  # a pole on the grid is NaN, as the reference returns nan for den == 0
+  acc = ab.FilterBank([1 / (1 - ab.z ** -1)])
+  r = acc.freq_response([0.0, 1.0])
+  assert np.isnan(r[0, 0]) and abs(r[0, 1] - 1 / (1 - np.exp(-1j))) < 1e-14
+
+
+def test_stream_valued_design_parameters_filter(ab, vectors):
+  """Builders called with Stream parameters (swept resonator / cutoff / decay) run through the
+  time-varying kernel path; outputs against the reference's (golden)."""
+  from test_designs import _tv_builders
+  xb = signal(10, 2500).tolist()
+  for key, make in _tv_builders(ab).items():
+    out = list(make()(xb))
+    assert len(out) == 2500
+    assert rel_err(out, vectors[key + "_y"]) <= TOL, key

@@ -242,6 +242,14 @@ def test_time_parallel_path(gpu, designs, monkeypatch):
     # state carry: a long block (chunked) followed by short ones (sequential) == one shot
     split = gpu.run(plan, x, xinit=xi, yinit=yi, splits=[131072 + 5, 1000, 200077 - 131077 - 1000])
     assert rel_err(split, fast) <= 3e-6
+  # up to one warp row of streams (32) takes this path, stream by stream
+  x = np.stack([signal(300 + i, 70000) for i in range(12)])
+  plan = gpu.capi.Plan(designs["bank_slaney"][:16])
+  fast = gpu.run(plan, x)
+  monkeypatch.setenv("ALZ_NO_TIME_PARALLEL", "1")
+  slow = gpu.run(plan, x)
+  monkeypatch.delenv("ALZ_NO_TIME_PARALLEL")
+  assert rel_err(fast, slow) <= 3e-6
 
 
 def test_host_path_time_segments(gpu, designs):
