@@ -64,7 +64,11 @@ struct AlzBiquadArgs {
 // sample; costs two extra float32 roundings, <= 1.8e-7 relative, still 50x inside the bar).
 // NB0: numerator taps of the FIRST section when it is longer than a biquad's (head FIR on
 // the input, e.g. gammatone.sampled's 8-tap first section); 0 = same as NB.
-template <int K, int NB, int MONIC, int NB0 = 0>
+// ZMASK: numerator taps that are zero in EVERY channel and are not computed at all (the
+// reference's Poly drops zero coefficients too): bit 2k = tap 1 of section k, bit 2k+1 = tap 2.
+// ALZ_ZMASK_KLAPURI is gammatone.klapuri's cascade [1 - z^-2, const, 1 - z^-2, const] / poles.
+#define ALZ_ZMASK_KLAPURI 0xDD
+template <int K, int NB, int MONIC, int NB0 = 0, int ZMASK = 0>
 struct AlzBiquadCore {
   static constexpr int H0 = ALZ_H0(NB0);
   static constexpr int NBF = NB0 > 3 ? NB0 : NB;   // taps of section 0
@@ -132,8 +136,8 @@ struct AlzBiquadCore {
   // One section's arithmetic.  in/in1/in2 = u_{k-1}[n], [n-1], [n-2].
   __device__ __forceinline__ double section(int k, double in, double in1, double in2, double y1, double y2) const {
     double t = MONIC ? in : b0[k] * in;
-    if (NB >= 2) t = fma(c1[k], in1, t);
-    if (NB >= 3) t = fma(c2[k], in2, t);
+    if (NB >= 2 && !((ZMASK >> (2 * k)) & 1)) t = fma(c1[k], in1, t);
+    if (NB >= 3 && !((ZMASK >> (2 * k + 1)) & 1)) t = fma(c2[k], in2, t);
     t = fma(na2[k], y2, t);
     return fma(na1[k], y1, t);
   }

@@ -52,6 +52,7 @@ struct HostPipe {   // lazily created resources of alz_apply_f32_host
 
 struct alz_plan {
   int kind = 0, C = 0, K = 0, NB = 0, NB0 = 0, monic = 0, device = 0, sm_count = 148;
+  int zmask = 0;               // biquad: numerator taps that are zero in every channel (AlzBiquadCore ZMASK)
   int xd = 0, yd = 0;          // history depths exposed to alz_state_init
   int state_doubles = 0;       // per recurrence
   int fp64_ops = 0;
@@ -100,11 +101,11 @@ static void keep_async_pool() {
 static const int kCoefSmall = 512, kCoefLarge = 3584;
 static const int kWarpsPerSm = 22;   // 2 x 4608 B tile buffers + 1 KB CTA reserve -> 22 CTAs per SM
 
-template <int K, int NB, int MONIC, int NCOEF, int NB0>
+template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
 __global__ void __launch_bounds__(32, kWarpsPerSm)
 alz_biquad_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca) {
   extern __shared__ __align__(16) float alz_smem[];
-  alz_run_warp<AlzBiquadCore<K, NB, MONIC, NB0>>(a, ca, alz_smem);
+  alz_run_warp<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>>(a, ca, alz_smem);
 }
 
 __global__ void __launch_bounds__(32)
@@ -115,12 +116,12 @@ alz_generic_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant_
 
 // TMA variants: same cores, tiles moved by cp.async.bulk.tensor (16-byte aligned rows only).
 static const int kWarpsPerSmTma = 24;
-template <int K, int NB, int MONIC, int NCOEF, int NB0>
+template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
 __global__ void __launch_bounds__(32, kWarpsPerSmTma)
 alz_biquad_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
                       const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
   extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
-  alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0>>(a, ca, &tmx, &tmy, alz_smem_tma);
+  alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>>(a, ca, &tmx, &tmy, alz_smem_tma);
 }
 
 __global__ void __launch_bounds__(32)
@@ -177,7 +178,7 @@ static bool make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMa
 }
 
 // One launch: channels [c0, c0+nch) x stream groups of `ta` (ta.S <= 65535*32 streams).
-template <int K, int NB, int MONIC, int NCOEF, int NB0>
+template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
 static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, int c0, int nch,
                                cudaStream_t st) {
   static AlzBiquadArgs<NCOEF> ca;   // too large for the stack of some callers; filled under a lock
@@ -211,42 +212,47 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
         nseg = 1;
       }
     }
-    alz_biquad_tma_kernel<K, NB, MONIC, NCOEF, NB0><<<dim3((unsigned)nch, (unsigned)(groups * nseg)), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
+    alz_biquad_tma_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, (unsigned)(groups * nseg)), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
     if (ta.sync) cudaFreeAsync(ta.sync, st);
   } else {
-    alz_biquad_kernel<K, NB, MONIC, NCOEF, NB0><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
+    alz_biquad_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
   }
   ALZ_CUDA(cudaGetLastError());
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ALZ_OK;
 }
 
-template <int K, int NB, int MONIC, int NB0>
+template <int K, int NB, int MONIC, int NB0, int ZMASK>
 static int launch_biquad_t(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
   const int stride = ALZ_COEF_STRIDE(K, NB0);
   const bool small = p->C * stride <= kCoefSmall;
   const int per_launch = (small ? kCoefSmall : kCoefLarge) / stride;
   for (int c0 = 0; c0 < p->C; c0 += per_launch) {
     const int nch = std::min(per_launch, p->C - c0);
-    const int rc = small ? launch_biquad_chunk<K, NB, MONIC, kCoefSmall, NB0>(p, ta, state, sstride, c0, nch, st)
-                         : launch_biquad_chunk<K, NB, MONIC, kCoefLarge, NB0>(p, ta, state, sstride, c0, nch, st);
+    const int rc = small ? launch_biquad_chunk<K, NB, MONIC, kCoefSmall, NB0, ZMASK>(p, ta, state, sstride, c0, nch, st)
+                         : launch_biquad_chunk<K, NB, MONIC, kCoefLarge, NB0, ZMASK>(p, ta, state, sstride, c0, nch, st);
     if (rc != ALZ_OK) return rc;
   }
   return ALZ_OK;
 }
 
-template <int K, int NB, int NB0>
+template <int K, int NB, int NB0, int ZMASK = 0>
 static int launch_biquad_nb(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
-  if (p->monic == 2) return launch_biquad_t<K, NB, 2, NB0>(p, ta, state, sstride, st);
-  if (p->monic == 1) return launch_biquad_t<K, NB, 1, NB0>(p, ta, state, sstride, st);
-  return launch_biquad_t<K, NB, 0, NB0>(p, ta, state, sstride, st);
+  if (p->monic == 2) return launch_biquad_t<K, NB, 2, NB0, ZMASK>(p, ta, state, sstride, st);
+  if (p->monic == 1) return launch_biquad_t<K, NB, 1, NB0, ZMASK>(p, ta, state, sstride, st);
+  return launch_biquad_t<K, NB, 0, NB0, ZMASK>(p, ta, state, sstride, st);
 }
 template <int K>
 static int launch_biquad_k(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
   switch (p->NB) {
     case 1: return launch_biquad_nb<K, 1, 0>(p, ta, state, sstride, st);
     case 2: return launch_biquad_nb<K, 2, 0>(p, ta, state, sstride, st);
-    default: return launch_biquad_nb<K, 3, 0>(p, ta, state, sstride, st);
+    default:
+      if constexpr (K == 4) {
+        if ((p->zmask & ALZ_ZMASK_KLAPURI) == ALZ_ZMASK_KLAPURI)
+          return launch_biquad_nb<4, 3, 0, ALZ_ZMASK_KLAPURI>(p, ta, state, sstride, st);
+      }
+      return launch_biquad_nb<K, 3, 0>(p, ta, state, sstride, st);
   }
 }
 // head-FIR plans: first section with up to 8 numerator taps (K in {1, 4}, NB in {1, 3})
@@ -414,6 +420,15 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
     }
     p->monic = monic ? (gain_in ? 2 : 1) : 0;
     p->fp64_ops = (monic ? K * (p->NB - 1 + 2) + (gain_in ? 0 : 1) : K * (p->NB + 2)) + (headfir ? 8 - p->NB : 0);
+    if (!headfir && !env_int("ALZ_NO_ZMASK", 0)) {   // taps 1 and 2 that no channel has (absent sections count as zero)
+      int zm = (1 << (2 * K)) - 1;
+      for (int c = 0; c < C; ++c)
+        for (size_t k = 0; k < secs[c].size(); ++k)
+          for (int j = 1; j <= 2; ++j)
+            if ((int)secs[c][k].b.size() > j && secs[c][k].b[j] != 0.0) zm &= ~(1 << (2 * (int)k + j - 1));
+      p->zmask = zm;
+      if (K == 4 && p->NB == 3 && (zm & ALZ_ZMASK_KLAPURI) == ALZ_ZMASK_KLAPURI) p->fp64_ops -= 6;   // the kernel that skips them
+    }
     const int stride = ALZ_COEF_STRIDE(K, p->NB0);
     p->h_tab.assign((size_t)C * stride, 0.0);
     p->sc.assign((size_t)C * (K + 1), 1.0);

@@ -277,3 +277,20 @@ def test_gain_modes(gpu, designs, monkeypatch):
   monkeypatch.delenv("ALZ_EXACT_GAIN")
   assert exact.fp64_ops == 13
   assert rel_err(gpu.run(exact, x), want) <= 6.5e-8   # = float32 rounding of the float64 result
+
+
+def test_structurally_zero_taps_are_skipped(gpu, designs, monkeypatch):
+  """gammatone.klapuri's sections are [1 - z^-2, const] / poles twice: the numerator taps that are
+  zero in every channel are not computed (10 instead of 16 float64 operations per channel-sample);
+  results are identical to the kernel that multiplies by the zeros."""
+  bank = designs["bank_klapuri"]
+  x = np.stack([signal(0, 8000), signal(7, 8000)])
+  lean = gpu.capi.Plan(bank)
+  assert lean.fp64_ops == 10
+  monkeypatch.setenv("ALZ_NO_ZMASK", "1")
+  full = gpu.capi.Plan(bank)
+  monkeypatch.delenv("ALZ_NO_ZMASK")
+  assert full.fp64_ops == 16
+  y = gpu.run(lean, x, splits=[3000, 5000])
+  assert np.array_equal(y, gpu.run(full, x))
+  assert rel_err(y, oracle.bank_apply(x, bank)) <= TOL

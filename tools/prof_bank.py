@@ -8,7 +8,11 @@ name, S, T, iters = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.arg
 C = int(sys.argv[5]) if len(sys.argv) > 5 else 64
 d = json.load(open("tests/golden/designs.json"))
 dev = torch.device("cuda:0"); torch.cuda.set_device(0)
-plan = _capi.Plan(d["bank_" + name][:C])
+if name.startswith("first"):      # "first1".."first4": only the first n sections of the slaney cascades (engine ceiling probes)
+  n = int(name[5:])
+  plan = _capi.Plan([ch[:n] for ch in d["bank_slaney"][:C]])
+else:
+  plan = _capi.Plan(d["bank_" + name][:C])
 xd = torch.rand((S, T), device=dev) * 2 - 1
 yd = torch.empty((S, C, T), dtype=torch.float32, device=dev)
 st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=dev)
