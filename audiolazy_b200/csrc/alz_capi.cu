@@ -195,6 +195,7 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
     // A launch of only a few waves of warps loses its last, partly filled wave: cut time into
     // segments chained through the state (alz_lane.cuh) so the next segment fills the tail.
     const long long warps = (long long)nch * groups, slots = (long long)p->sm_count * kWarpsPerSmTma;
+    ta.paired = env_int("ALZ_TMA_PAIRED", warps >= slots ? 1 : 0);
     long long nseg = 1;
     if (warps > slots && warps < 8 * slots && ta.T >= 2048 && !env_int("ALZ_NO_SEGMENT", 0)) {
       const long long waves = env_int("ALZ_SEG_WAVES", 16), min_len = env_int("ALZ_SEG_MIN", 1024);

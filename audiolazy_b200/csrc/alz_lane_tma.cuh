@@ -101,7 +101,8 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   const int swz = lane & 7;
   float* const myrow = reinterpret_cast<float*>(smem) + lane * 32;
 
-  if (lane == 0) {   // tile 0 in flight
+  const bool paired = a.paired != 0;
+  if (lane == 0 && !paired) {   // tile 0 in flight
     alz_mbar_expect_tx(mbar0, ALZ_TMA_TILE_BYTES);
     alz_tma_load_2d(tile0, tmx, tb, (int)s0, mbar0);
   }
@@ -109,13 +110,28 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   for (int i = 0; i < ntiles; ++i) {
     const int b = i & 1;
     const int t0 = i * ALZ_TT;
-    if (lane == 0 && i + 1 < ntiles) {
-      // Prefetch tile i+1 into the other buffer.  That buffer was the source of the TMA
-      // store of tile i-1: wait until the store has finished READING it (it was issued a
-      // whole barrier-wait ago, so this normally does not block).
-      if (i >= 1) alz_bulk_wait_read0();
-      alz_mbar_expect_tx(mbar0 + 8 * (b ^ 1), ALZ_TMA_TILE_BYTES);
-      alz_tma_load_2d(tile0 + (b ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, (int)s0, mbar0 + 8 * (b ^ 1));
+    if (lane == 0) {
+      if (paired) {
+        // Tiles go in pairs: both loads are issued together once the previous pair's stores have
+        // been read out of shared memory, and both stores are issued back to back after the second
+        // tile, so each output row receives 256 contiguous bytes at (nearly) the same time.
+        if (b == 0) {
+          if (i >= 2) alz_bulk_wait_read0();
+          alz_mbar_expect_tx(mbar0, ALZ_TMA_TILE_BYTES);
+          alz_tma_load_2d(tile0, tmx, tb + t0, (int)s0, mbar0);
+          if (i + 1 < ntiles) {
+            alz_mbar_expect_tx(mbar0 + 8, ALZ_TMA_TILE_BYTES);
+            alz_tma_load_2d(tile0 + ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, (int)s0, mbar0 + 8);
+          }
+        }
+      } else if (i + 1 < ntiles) {
+        // Prefetch tile i+1 into the other buffer.  That buffer was the source of the TMA
+        // store of tile i-1: wait until the store has finished READING it (it was issued a
+        // whole barrier-wait ago, so this normally does not block).
+        if (i >= 1) alz_bulk_wait_read0();
+        alz_mbar_expect_tx(mbar0 + 8 * (b ^ 1), ALZ_TMA_TILE_BYTES);
+        alz_tma_load_2d(tile0 + (b ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, (int)s0, mbar0 + 8 * (b ^ 1));
+      }
     }
     alz_mbar_wait(mbar0 + 8 * b, (i >> 1) & 1);     // tile i has landed (async proxy writes visible after the wait)
     const int nvalid = i < nfull ? ALZ_TT : (int)(tlen - t0);
@@ -123,8 +139,14 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
     alz_fence_async_smem();                          // my generic-proxy writes -> visible to the TMA store
     __syncwarp();
     if (lane == 0) {
-      alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
-      alz_bulk_commit();
+      if (!paired) {
+        alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
+        alz_bulk_commit();
+      } else if (b == 1 || i + 1 == ntiles) {
+        if (b == 1) alz_tma_store_3d(tmy, tb + t0 - ALZ_TT, c, (int)s0, tile0);
+        alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
+        alz_bulk_commit();
+      }
     }
   }
   if (lane == 0) alz_bulk_wait0();                   // all output tiles are globally written before exit
