@@ -138,13 +138,21 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
     core.tile(myrow + b * (ALZ_TMA_TILE_BYTES / 4), swz, nvalid, t0);
     alz_fence_async_smem();                          // my generic-proxy writes -> visible to the TMA store
     __syncwarp();
+    // The TMA clips a box at 16-byte granularity: when n_samples is not a multiple of 4 the ragged
+    // last tile is written by the lanes themselves (plain stores of the valid samples only).
+    const bool by_lanes = nvalid < ALZ_TT && (a.T & 3) != 0;
+    if (by_lanes && valid) {
+      const float* src = myrow + b * (ALZ_TMA_TILE_BYTES / 4);
+      float* dst = a.y + s * a.ysS + (long long)c * a.ys + tbeg + t0;
+      for (int j = 0; j < nvalid; ++j) dst[j] = src[(((j >> 2) ^ swz) << 2) | (j & 3)];
+    }
     if (lane == 0) {
       if (!paired) {
-        alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
+        if (!by_lanes) alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
         alz_bulk_commit();
       } else if (b == 1 || i + 1 == ntiles) {
         if (b == 1) alz_tma_store_3d(tmy, tb + t0 - ALZ_TT, c, (int)s0, tile0);
-        alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
+        if (!by_lanes) alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
         alz_bulk_commit();
       }
     }

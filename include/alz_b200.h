@@ -142,7 +142,7 @@ int32_t alz_plan_history(const alz_plan* plan, int32_t* xd, int32_t* yd);
  * channel-minor) of n_samples float32, row stride y_stride elements.
  * state_dev: in/out, carries every recurrence across blocks, so that
  * apply(block0) ; apply(block1) == apply(block0 ++ block1) bit for bit.  (Exception: calls
- * with <= 8 streams of >= 65536 samples are evaluated time-parallel -- zero-state chunks,
+ * with <= 32 streams of >= 65536 samples are evaluated time-parallel -- zero-state chunks,
  * transition matrices, scan, replay -- and agree with the sequential result to float64
  * rounding of the chunk states, ~1e-6 relative at worst; ALZ_NO_TIME_PARALLEL=1 disables it.)
  * Asynchronous on `cuda_stream`.

@@ -294,3 +294,25 @@ def test_structurally_zero_taps_are_skipped(gpu, designs, monkeypatch):
   y = gpu.run(lean, x, splits=[3000, 5000])
   assert np.array_equal(y, gpu.run(full, x))
   assert rel_err(y, oracle.bank_apply(x, bank)) <= TOL
+
+
+def test_row_padding_is_never_written(gpu, designs):
+  """Rows wider than n_samples (16-byte aligned strides, so the TMA engine runs): nothing outside
+  [0, n_samples) of an output row may be written, whatever n_samples % 4 is (the TMA clips a box at
+  16-byte granularity, so ragged ends are stored by the lanes)."""
+  torch = gpu.torch
+  bank = designs["bank_slaney"][:5]
+  plan = gpu.capi.Plan(bank)
+  cur = torch.cuda.current_stream().cuda_stream
+  for S, T in [(37, 2125), (3, 77), (33, 33), (2, 5), (40, 64 + 2), (5, 96)]:
+    x = np.stack([signal(500 + i, T) for i in range(S)])
+    want = gpu.run(plan, x)
+    stride = (T + 3) // 4 * 4 + 8
+    xs = torch.zeros((S, stride), device=gpu.dev)
+    xs[:, :T] = torch.from_numpy(x).to(gpu.dev)
+    ys = torch.full((S, len(bank), stride), float("nan"), device=gpu.dev)
+    st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=gpu.dev)
+    plan.apply(xs.data_ptr(), ys.data_ptr(), st.data_ptr(), S, T, stride, stride, cur)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(ys[:, :, T:]).all()), (S, T)
+    assert np.array_equal(ys[:, :, :T].cpu().numpy(), want), (S, T)
