@@ -198,7 +198,7 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
     ta.paired = env_int("ALZ_TMA_PAIRED", warps >= slots ? 1 : 0);
     long long nseg = 1;
     if (warps > slots && warps < 8 * slots && ta.T >= 2048 && !env_int("ALZ_NO_SEGMENT", 0)) {
-      const long long waves = env_int("ALZ_SEG_WAVES", 16), min_len = env_int("ALZ_SEG_MIN", 1024);
+      const long long waves = std::max(1, env_int("ALZ_SEG_WAVES", 16)), min_len = std::max(32, env_int("ALZ_SEG_MIN", 1024));
       nseg = std::min((waves * slots + warps - 1) / warps, ta.T / min_len);
       const long long len = ((ta.T + nseg - 1) / nseg + 31) / 32 * 32;
       nseg = (ta.T + len - 1) / len;
@@ -207,7 +207,10 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
         unsigned* sync = nullptr;
         keep_async_pool();
         ALZ_CUDA(cudaMallocAsync(&sync, words * 4, st));
-        ALZ_CUDA(cudaMemsetAsync(sync, 0, words * 4, st));
+        if (cudaMemsetAsync(sync, 0, words * 4, st) != cudaSuccess) {
+          cudaFreeAsync(sync, st);
+          ALZ_CUDA(cudaGetLastError());
+        }
         ta.nseg = (int)nseg; ta.groups = (int)groups; ta.seg_len = len; ta.sync = sync;
       } else {
         nseg = 1;
