@@ -102,6 +102,7 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   float* const myrow = reinterpret_cast<float*>(smem) + lane * 32;
 
   const bool paired = a.paired != 0;
+  const bool tail_by_lanes = (a.T & 3) != 0 && nfull < ntiles;
   if (lane == 0 && !paired) {   // tile 0 in flight
     alz_mbar_expect_tx(mbar0, ALZ_TMA_TILE_BYTES);
     alz_tma_load_2d(tile0, tmx, tb, (int)s0, mbar0);
@@ -138,14 +139,7 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
     core.tile(myrow + b * (ALZ_TMA_TILE_BYTES / 4), swz, nvalid, t0);
     alz_fence_async_smem();                          // my generic-proxy writes -> visible to the TMA store
     __syncwarp();
-    // The TMA clips a box at 16-byte granularity: when n_samples is not a multiple of 4 the ragged
-    // last tile is written by the lanes themselves (plain stores of the valid samples only).
-    const bool by_lanes = nvalid < ALZ_TT && (a.T & 3) != 0;
-    if (by_lanes && valid) {
-      const float* src = myrow + b * (ALZ_TMA_TILE_BYTES / 4);
-      float* dst = a.y + s * a.ysS + (long long)c * a.ys + tbeg + t0;
-      for (int j = 0; j < nvalid; ++j) dst[j] = src[(((j >> 2) ^ swz) << 2) | (j & 3)];
-    }
+    const bool by_lanes = tail_by_lanes && i + 1 == ntiles;   // ragged last tile: stored after the loop
     if (lane == 0) {
       if (!paired) {
         if (!by_lanes) alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
@@ -156,6 +150,14 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
         alz_bulk_commit();
       }
     }
+  }
+  if (tail_by_lanes && valid) {
+    // The TMA clips a box at 16-byte granularity: when n_samples is not a multiple of 4 the ragged
+    // last tile is written by the lanes themselves (plain stores of the valid samples only).
+    const int i = ntiles - 1, t0 = i * ALZ_TT, nvalid = (int)(tlen - t0);
+    const float* src = myrow + (i & 1) * (ALZ_TMA_TILE_BYTES / 4);
+    float* dst = a.y + s * a.ysS + (long long)c * a.ys + tbeg + t0;
+    for (int j = 0; j < nvalid; ++j) dst[j] = src[(((j >> 2) ^ swz) << 2) | (j & 3)];
   }
   if (lane == 0) alz_bulk_wait0();                   // all output tiles are globally written before exit
   if (valid) core.store(ca, r, tlen);
