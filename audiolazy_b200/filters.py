@@ -54,38 +54,20 @@ class LinearFilterProperties(object):
   """Coefficient read-out shared by filters and filter lists; needs ``numpoly`` and
   ``denpoly`` (reference ``lazy_filters.py:47-95``)."""
 
-  @property
-  def numlist(self):
-    if any(power < 0 for power, _ in self.numpoly.terms()):
+  def _dense(self, poly):
+    """Coefficients of ``poly`` by ascending delay, zeros included; non-causal filters raise."""
+    if any(power < 0 for power, _ in poly.terms()):
       raise ValueError("Non-causal filter")
-    return list(self.numpoly.values())
+    return list(poly.values())
 
-  numerator = numlist
-
-  @property
-  def denlist(self):
-    if any(power < 0 for power, _ in self.denpoly.terms()):
-      raise ValueError("Non-causal filter")
-    return list(self.denpoly.values())
-
-  denominator = denlist
-
-  @property
-  def numdict(self):
-    return OrderedDict(self.numpoly.terms())
-
-  @property
-  def dendict(self):
-    return OrderedDict(self.denpoly.terms())
-
-  @property
-  def numpolyz(self):
-    """Numerator as a polynomial in ``z`` (for root finding)."""
-    return Poly(self.numerator[::-1])
-
-  @property
-  def denpolyz(self):
-    return Poly(self.denominator[::-1])
+  numlist = numerator = property(lambda self: self._dense(self.numpoly))
+  denlist = denominator = property(lambda self: self._dense(self.denpoly))
+  #: delay -> coefficient, non-zero terms only, in ascending delay order
+  numdict = property(lambda self: OrderedDict(self.numpoly.terms()))
+  dendict = property(lambda self: OrderedDict(self.denpoly.terms()))
+  #: the same polynomials written in ``z`` instead of ``z**-1`` (for root finding)
+  numpolyz = property(lambda self: Poly(self.numerator[::-1]))
+  denpolyz = property(lambda self: Poly(self.denominator[::-1]))
 
 
 def _is_real_number(value):
@@ -121,37 +103,32 @@ class LinearFilter(LinearFilterProperties):
   """Rational transfer function ``numpoly / denpoly`` in ``x = z**-1``."""
 
   def __init__(self, numerator=None, denominator=None):
-    if isinstance(numerator, LinearFilter):
-      if denominator is not None:
-        numerator = operator.truediv(numerator, denominator)
-      self.numpoly = numerator.numpoly
-      self.denpoly = numerator.denpoly
+    if isinstance(numerator, LinearFilter):      # copy constructor, optionally divided by `denominator`
+      source = numerator if denominator is None else operator.truediv(numerator, denominator)
+      num, den = source.numpoly, source.denpoly
     else:
-      self.numpoly = Poly(numerator)
-      self.denpoly = Poly({0: 1} if denominator is None else denominator)
-    # the denominator's lowest power becomes z**0 (reference lazy_filters.py:126-132)
-    power = min(p for p, _ in self.denpoly.terms())
-    if power != 0:
-      shift = Poly([0, 1]) ** -power
-      self.numpoly = self.numpoly * shift
-      self.denpoly = self.denpoly * shift
+      num, den = Poly(numerator), Poly({0: 1} if denominator is None else denominator)
+    # normalise so that the denominator's lowest power is z**0 (reference lazy_filters.py:126-132)
+    lowest = min(power for power, _ in den.terms())
+    if lowest != 0:
+      advance = Poly([0, 1]) ** -lowest
+      num, den = num * advance, den * advance
+    self.numpoly, self.denpoly = num, den
+
+  def _polys(self):
+    return self.numpoly, self.denpoly
 
   def __iter__(self):
-    yield self.numdict
-    yield self.dendict
+    return iter((self.numdict, self.dendict))
 
   def __hash__(self):
-    return hash(tuple(self.numdict) + tuple(self.dendict))
+    return hash(tuple(power for poly in self._polys() for power, _ in poly.terms()))
 
   def __eq__(self, other):
-    if isinstance(other, LinearFilter):
-      return self.numpoly == other.numpoly and self.denpoly == other.denpoly
-    return False
+    return isinstance(other, LinearFilter) and all(mine == theirs for mine, theirs in zip(self._polys(), other._polys()))
 
-  def __ne__(self, other):
-    if isinstance(other, LinearFilter):
-      return self.numpoly != other.numpoly and self.denpoly != other.denpoly
-    return False
+  def __ne__(self, other):   # as in the reference: true only when BOTH polynomials differ
+    return isinstance(other, LinearFilter) and all(mine != theirs for mine, theirs in zip(self._polys(), other._polys()))
 
   # -- the hot path ------------------------------------------------------------------
   def _check_callable(self):
@@ -310,12 +287,13 @@ class ZFilter(LinearFilter):
   def __rtruediv__(self, other):
     return self._wrap(other) / self
 
-  def __pow__(self, other):
-    if (other < 0) and (len(self.numpoly) >= 2 or len(self.denpoly) >= 2):
-      return ZFilter(self.denpoly, self.numpoly) ** -other
-    if isinstance(other, (int, float)):
-      return ZFilter(self.numpoly ** other, self.denpoly ** other)
-    raise ValueError("Z-transform powers only valid with integers")
+  def __pow__(self, exponent):
+    single_terms = len(self.numpoly) < 2 and len(self.denpoly) < 2
+    if exponent < 0 and not single_terms:      # invert first: Poly powers of sums need exponent >= 0
+      return ZFilter(self.denpoly, self.numpoly) ** -exponent
+    if not isinstance(exponent, (int, float)):
+      raise ValueError("Z-transform powers only valid with integers")
+    return ZFilter(self.numpoly ** exponent, self.denpoly ** exponent)
 
   def __neg__(self):
     return ZFilter(-self.numpoly, self.denpoly)
@@ -406,10 +384,10 @@ class FilterList(list, LinearFilterProperties):
     return all(f.is_causal() for f in self.callables if hasattr(f, "is_causal"))
 
   def __eq__(self, other):
-    return type(self) == type(other) and list.__eq__(self, other)
+    return type(other) is type(self) and list(self) == list(other)
 
   def __ne__(self, other):
-    return type(self) != type(other) or list.__ne__(self, other)
+    return not self == other
 
   __hash__ = None
 
@@ -417,6 +395,19 @@ class FilterList(list, LinearFilterProperties):
   def callables(self):
     """Members, with bare numbers cast to constant-gain filters."""
     return [(f if callable(f) else LinearFilter(f)) for f in self]
+
+  def _fold(self, combine, attribute):
+    """``combine`` over one attribute of every member; members without it are non-linear."""
+    try:
+      return reduce(combine, (getattr(f, attribute) for f in self.callables))
+    except AttributeError:
+      raise AttributeError("Non-linear filter")
+
+  def _roots(self, attribute):
+    """All members' ``poles`` / ``zeros`` concatenated (LTI lists only)."""
+    if not self.is_lti():
+      raise AttributeError("Not a LTI filter")
+    return [root for f in self.callables for root in getattr(f, attribute)]
 
   def _flat_sections(self):
     """Sections of an all-LTI list whose members are filters or cascades, else None."""
@@ -464,35 +455,15 @@ class CascadeFilter(FilterList):
   apply = LinearFilter.apply
   apply_host = LinearFilter.apply_host
 
-  @property
-  def numpoly(self):
-    try:
-      return reduce(operator.mul, (f.numpoly for f in self.callables))
-    except AttributeError:
-      raise AttributeError("Non-linear filter")
-
-  @property
-  def denpoly(self):
-    try:
-      return reduce(operator.mul, (f.denpoly for f in self.callables))
-    except AttributeError:
-      raise AttributeError("Non-linear filter")
+  # the cascade as one transfer function: products of the members' polynomials / responses
+  numpoly = property(lambda self: self._fold(operator.mul, "numpoly"))
+  denpoly = property(lambda self: self._fold(operator.mul, "denpoly"))
+  poles = property(lambda self: self._roots("poles"))
+  zeros = property(lambda self: self._roots("zeros"))
 
   @elementwise("freq", 1)
   def freq_response(self, freq):
     return reduce(operator.mul, (f.freq_response(freq) for f in self.callables))
-
-  @property
-  def poles(self):
-    if not self.is_lti():
-      raise AttributeError("Not a LTI filter")
-    return reduce(operator.concat, (f.poles for f in self.callables))
-
-  @property
-  def zeros(self):
-    if not self.is_lti():
-      raise AttributeError("Not a LTI filter")
-    return reduce(operator.concat, (f.zeros for f in self.callables))
 
 
 @avoid_stream
@@ -513,34 +484,25 @@ class ParallelFilter(FilterList):
     arg0 = thub(args[0], len(self))
     return reduce(operator.add, (f(arg0, *args[1:], **kwargs) for f in self.callables))
 
-  @property
-  def numpoly(self):
+  def _as_one_filter(self):
     if not self.is_linear():
       raise AttributeError("Non-linear filter")
-    return reduce(operator.add, (ZFilter(f) for f in self.callables)).numpoly
+    return reduce(operator.add, (ZFilter(f) for f in self.callables))
 
-  @property
-  def denpoly(self):
-    try:
-      return reduce(operator.mul, (f.denpoly for f in self.callables))
-    except AttributeError:
-      raise AttributeError("Non-linear filter")
-
-  @elementwise("freq", 1)
-  def freq_response(self, freq):
-    return reduce(operator.add, (f.freq_response(freq) for f in self.callables))
-
-  @property
-  def poles(self):
-    if not self.is_lti():
-      raise AttributeError("Not a LTI filter")
-    return reduce(operator.concat, (f.poles for f in self.callables))
+  # the sum as one transfer function: summed over a common denominator
+  numpoly = property(lambda self: self._as_one_filter().numpoly)
+  denpoly = property(lambda self: self._fold(operator.mul, "denpoly"))
+  poles = property(lambda self: self._roots("poles"))
 
   @property
   def zeros(self):
     if not self.is_lti():
       raise AttributeError("Not a LTI filter")
     return reduce(operator.add, (ZFilter(f) for f in self)).zeros
+
+  @elementwise("freq", 1)
+  def freq_response(self, freq):
+    return reduce(operator.add, (f.freq_response(freq) for f in self.callables))
 
 
 # --------------------------------------------------------------------------------------

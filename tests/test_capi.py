@@ -42,15 +42,18 @@ def test_sass_is_sm100a_with_fp64_and_uniform_operands():
   assert "sm_100a" in out
   # stream the SASS and stop as soon as both signatures have been seen
   proc = subprocess.Popen([cuobjdump, "-sass", _build.LIB_PATH], stdout=subprocess.PIPE, text=True)
-  seen_ur = seen_cp = False
+  seen_ur = seen_cp = seen_tma_ld = seen_tma_st = False
   for line in proc.stdout:
     seen_ur = seen_ur or re.search(r"DFMA R\d+, R\d+(\.reuse)?, UR\d+, R\d+", line) is not None
-    seen_cp = seen_cp or "LDGSTS" in line          # cp.async staging
-    if seen_ur and seen_cp:
+    seen_cp = seen_cp or "LDGSTS" in line          # cp.async staging (fallback engine)
+    seen_tma_ld = seen_tma_ld or "UTMALDG" in line  # TMA tile load
+    seen_tma_st = seen_tma_st or "UTMASTG" in line  # TMA tile store
+    if seen_ur and seen_cp and seen_tma_ld and seen_tma_st:
       break
   proc.kill()
   assert seen_ur, "coefficients are not in uniform registers"
   assert seen_cp, "no cp.async (LDGSTS) in the kernels"
+  assert seen_tma_ld and seen_tma_st, "no TMA tile load/store (UTMALDG/UTMASTG) in the kernels"
 
 
 def test_pack_sections_layout():
