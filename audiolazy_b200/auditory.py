@@ -26,19 +26,23 @@ __all__ = ["erb", "gammatone", "gammatone_erb_constants", "erb_space", "gammaton
 erb = StrategyDict("erb")
 
 
+def _in_hertz(freq, Hz):
+  """``(frequency in Hz, unit)``; without a unit the argument must already be in Hz."""
+  if Hz is None:
+    if freq < 7:   # looks like rad/sample (anything up to 2 * pi)
+      raise ValueError("Frequency out of range.")
+    return freq / 1, 1
+  return freq / Hz, Hz
+
+
 @erb.strategy("gm90", "glasberg_moore_90", "glasberg_moore")
 @elementwise("freq", 0)
 def erb(freq, Hz=None):
   """Equivalent rectangular bandwidth, Glasberg & Moore (1990): ``24.7 (4.37e-3 f + 1)``.
   ``freq`` in Hz, or in rad/sample when ``Hz = sHz(rate)[1]`` is given (the result is then
   in rad/sample too). Reference ``lazy_auditory.py:55-70``."""
-  if Hz is None:
-    if freq < 7:   # perhaps the user tried something up to 2 * pi
-      raise ValueError("Frequency out of range.")
-    Hz = 1
-  fHz = freq / Hz
-  result = 24.7 * (4.37e-3 * fHz + 1.)
-  return result * Hz
+  hertz, unit = _in_hertz(freq, Hz)
+  return 24.7 * (4.37e-3 * hertz + 1.) * unit
 
 
 @erb.strategy("mg83", "moore_glasberg_83")
@@ -46,13 +50,8 @@ def erb(freq, Hz=None):
 def erb(freq, Hz=None):
   """Equivalent rectangular bandwidth, Moore & Glasberg (1983):
   ``6.23e-6 f**2 + 93.39e-3 f + 28.52``. Reference ``lazy_auditory.py:73-88``."""
-  if Hz is None:
-    if freq < 7:
-      raise ValueError("Frequency out of range.")
-    Hz = 1
-  fHz = freq / Hz
-  result = 6.23e-6 * fHz ** 2 + 93.39e-3 * fHz + 28.52
-  return result * Hz
+  hertz, unit = _in_hertz(freq, Hz)
+  return (6.23e-6 * hertz ** 2 + 93.39e-3 * hertz + 28.52) * unit
 
 
 def gammatone_erb_constants(n):
@@ -89,15 +88,16 @@ def gammatone(freq, bandwidth, phase=0, eta=4):
 def gammatone(freq, bandwidth):
   """Slaney's (1993) cascade of four one-zero two-pole sections; reference
   ``lazy_auditory.py:185-202``."""
-  A = exp(-bandwidth)
-  cosw = cos(freq)
-  sinw = sin(freq)
-  sig = [1., -1.]
-  coeff = [cosw + s1 * (sqrt(2) + s2) * sinw for s1 in sig for s2 in sig]
-  numerator = [1 - A * c * z ** -1 for c in coeff]
-  denominator = 1 - 2 * A * cosw * z ** -1 + A ** 2 * z ** -2
-  filt = CascadeFilter(num / denominator for num in numerator)
-  return CascadeFilter(f / abs(f.freq_response(freq)) for f in filt)
+  radius = exp(-bandwidth)
+  c, s = cos(freq), sin(freq)
+  poles = 1 - 2 * radius * c * z ** -1 + radius ** 2 * z ** -2        # shared by the four sections
+  sections = []
+  for outer in (1., -1.):
+    for inner in (1., -1.):
+      zero = c + outer * (sqrt(2) + inner) * s                        # cos w +- (sqrt 2 +- 1) sin w
+      section = (1 - radius * zero * z ** -1) / poles
+      sections.append(section / abs(section.freq_response(freq)))     # 0 dB at the centre frequency
+  return CascadeFilter(sections)
 
 
 @gammatone.strategy("klapuri")

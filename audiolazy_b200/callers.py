@@ -87,20 +87,22 @@ maverage = StrategyDict("maverage")
 @maverage.strategy("deque")
 def maverage(size):
   """Running mean with a deque (the reference's only non-ZFilter strategy; host-side)."""
-  size_inv = 1. / size
+  scale = 1. / size
 
   @tostream
-  def maverage_filter(sig, zero=0.):
-    data = deque((zero * size_inv for _ in range(size)), maxlen=size)
-    mean_value = zero
-    for el in sig:
-      mean_value -= data.popleft()
-      new_value = el * size_inv
-      data.append(new_value)
-      mean_value += new_value
-      yield mean_value
+  def running_mean(sig, zero=0.):
+    # the window holds the already scaled samples; the running total drops the oldest and adds
+    # the newest (same operation order as the reference, so results are bit-identical)
+    window = deque([zero * scale] * size)
+    total = zero
+    for sample in sig:
+      total -= window.popleft()
+      scaled = sample * scale
+      window.append(scaled)
+      total += scaled
+      yield total
 
-  return maverage_filter
+  return running_mean
 
 
 @maverage.strategy("recursive", "feedback")
