@@ -172,10 +172,13 @@ def run_reference(args):
   value = sum(values) / len(values)
   line = {
     "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-    "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "warmup": args.warmup, "ms_per_step": args.streams * args.samples / value * 1e3, "higher_is_better": True,
+    "scaling": "weak", "vs_baseline": None,
     "dtype": "f64", "data": "synthetic",
     "config": {"workload": "64-ch gammatone ERB bank (%s), fs 48 kHz, CPU port of the reference evaluator on a "
-                           "bounded sample of the %d x %d stream batch" % (args.strategy, args.streams, args.samples)},
+                           "bounded sample of the %d x %d stream batch" % (args.strategy, args.streams, args.samples),
+               "ms_per_step_note": "extrapolated from the sample to the whole batch (streams are independent: the "
+                                   "cost is linear in their number)"},
     "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "gpu_launches": 0,
