@@ -124,6 +124,17 @@ alz_biquad_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_consta
   alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>>(a, ca, &tmx, &tmy, alz_smem_tma);
 }
 
+// EXPERIMENTAL (ALZ_WARPS_PER_CTA=3): three independent warps per CTA, same channel, consecutive stream
+// groups / tickets: 9 CTAs x 3 warps = 27 warps per SM instead of 24 (one 1 KB reserve per 3 warps).
+static const int kWarpsPerCtaWide = 3;
+template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
+__global__ void __launch_bounds__(32 * kWarpsPerCtaWide, 9)
+alz_biquad_tma_wide_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
+                           const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
+  extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
+  alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>, AlzBiquadArgs<NCOEF>, kWarpsPerCtaWide>(a, ca, &tmx, &tmy, alz_smem_tma);
+}
+
 __global__ void __launch_bounds__(32)
 alz_generic_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzGenericArgs ca,
                        const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
@@ -216,7 +227,23 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
         nseg = 1;
       }
     }
-    alz_biquad_tma_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, (unsigned)(groups * nseg)), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
+    ta.groups = (int)groups;
+    bool wide = false;
+    if constexpr (K == 4 && NB0 == 0 && NCOEF == kCoefLarge) wide = env_int("ALZ_WARPS_PER_CTA", 1) == kWarpsPerCtaWide;
+    if (wide) {
+      if constexpr (K == 4 && NB0 == 0 && NCOEF == kCoefLarge) {
+        const unsigned gy = (unsigned)((groups * nseg + kWarpsPerCtaWide - 1) / kWarpsPerCtaWide);
+        const size_t smem = (size_t)kWarpsPerCtaWide * (2 * ALZ_TMA_TILE_BYTES + 16);
+        static std::once_flag attr;
+        std::call_once(attr, [smem] {
+          cudaFuncSetAttribute(alz_biquad_tma_wide_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        });
+        alz_biquad_tma_wide_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, gy), 32 * kWarpsPerCtaWide, smem, st>>>(ta, ca, tmx, tmy);
+      }
+    } else {
+      alz_biquad_tma_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, (unsigned)(groups * nseg)), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
+    }
     if (ta.sync) cudaFreeAsync(ta.sync, st);
   } else {
     alz_biquad_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);

@@ -51,21 +51,32 @@ __device__ __forceinline__ void alz_bulk_wait_read0() { asm volatile("cp.async.b
 __device__ __forceinline__ void alz_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void alz_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-template <class Core, class CoreArgs>
+// W = warps per CTA.  Every warp is an independent worker with its own tiles and mbarriers (no CTA
+// barrier anywhere); W > 1 only amortises the 1 KB of shared memory the system reserves per CTA
+// (W = 3: 27 warps per SM instead of 24).  All warps of a CTA share the channel (blockIdx.x).
+// EXPERIMENTAL for W > 1 (ALZ_WARPS_PER_CTA=3): not yet measured on hardware.
+template <class Core, class CoreArgs, int W = 1>
 __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const CoreArgs& ca, const CUtensorMap* tmx,
                                                  const CUtensorMap* tmy, unsigned char* smem) {
-  const int lane = threadIdx.x;
+  const int lane = W == 1 ? threadIdx.x : (threadIdx.x & 31);
+  const int warp = W == 1 ? 0 : (threadIdx.x >> 5);
   const int c_local = blockIdx.x;              // CTA-uniform: coefficients go to uniform registers
   const int c = a.c_base + c_local;
-  int group = blockIdx.y, seg = 0;
+  int group = W == 1 ? blockIdx.y : blockIdx.y * W + warp, seg = 0;
   long long tbeg = 0, tlen = a.T;
   unsigned* flag = nullptr;
+  if constexpr (W > 1) {
+    if (a.nseg <= 1 && group >= a.groups) return;   // surplus warp of the last CTA
+  }
   if (a.nseg > 1) {
     // Ticket order = start order within the channel, so the CTA that owns the previous segment
     // of my (channel, group) is already running or done: the wait below cannot deadlock.
     unsigned ticket = 0;
     if (lane == 0) ticket = atomicAdd(a.sync + c_local, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if constexpr (W > 1) {
+      if (ticket >= (unsigned)a.groups * (unsigned)a.nseg) return;
+    }
     seg = (int)(ticket / (unsigned)a.groups);
     group = (int)(ticket - (unsigned)seg * (unsigned)a.groups);
     tbeg = (long long)seg * a.seg_len;
@@ -83,8 +94,10 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   const bool valid = s < a.S;
   const long long r = (long long)c * a.Stot + (valid ? s : a.S - 1);   // stream-fastest: coalesced state access
 
+  if constexpr (W > 1) smem += warp * (2 * ALZ_TMA_TILE_BYTES);   // tiles of all warps first (1024-byte aligned) ...
   const unsigned tile0 = alz_smem_u32(smem);
-  const unsigned mbar0 = tile0 + 2 * ALZ_TMA_TILE_BYTES;
+  const unsigned mbar0 = W == 1 ? tile0 + 2 * ALZ_TMA_TILE_BYTES                                   // ... mbarriers after them
+                                : tile0 + (W - warp) * (2 * ALZ_TMA_TILE_BYTES) + warp * 16;
   if (lane == 0) {
     alz_mbar_init(mbar0, 1);
     alz_mbar_init(mbar0 + 8, 1);
