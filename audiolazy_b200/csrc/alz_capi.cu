@@ -4,6 +4,7 @@
 #include "alz_biquad.cuh"
 #include "alz_generic.cuh"
 #include "alz_lane_tma.cuh"
+#include "alz_lane_tma_wide.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCtaWide, 9)
 alz_biquad_tma_wide_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
                            const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
   extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
-  alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>, AlzBiquadArgs<NCOEF>, kWarpsPerCtaWide>(a, ca, &tmx, &tmy, alz_smem_tma);
+  alz_run_warps_tma_wide<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>, AlzBiquadArgs<NCOEF>, kWarpsPerCtaWide>(a, ca, &tmx, &tmy, alz_smem_tma);
 }
 
 __global__ void __launch_bounds__(32)
@@ -229,9 +230,11 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state,
     }
     ta.groups = (int)groups;
     bool wide = false;
-    if constexpr (K == 4 && NB0 == 0 && NCOEF == kCoefLarge) wide = env_int("ALZ_WARPS_PER_CTA", 1) == kWarpsPerCtaWide;
+    // only the instantiations that fit 72 registers without spills (gammatone banks in gain mode 2)
+    constexpr bool kHasWide = K == 4 && NB0 == 0 && NCOEF == kCoefLarge && MONIC == 2 && (NB <= 2 || ZMASK != 0);
+    if constexpr (kHasWide) wide = env_int("ALZ_WARPS_PER_CTA", 1) == kWarpsPerCtaWide;
     if (wide) {
-      if constexpr (K == 4 && NB0 == 0 && NCOEF == kCoefLarge) {
+      if constexpr (kHasWide) {
         const unsigned gy = (unsigned)((groups * nseg + kWarpsPerCtaWide - 1) / kWarpsPerCtaWide);
         const size_t smem = (size_t)kWarpsPerCtaWide * (2 * ALZ_TMA_TILE_BYTES + 16);
         static std::once_flag attr;

@@ -1,75 +1,42 @@
-// alz_lane_tma.cuh -- the "lane = stream" engine with TMA tile movement (sm_100a).
+// alz_lane_tma_wide.cuh -- EXPERIMENTAL variant of the TMA tile engine with W warps per CTA.
 //
-// Same decomposition as alz_lane.cuh (CTA = warp = (channel, 32 streams), tiles of 32
-// samples filtered in place), but the tile is moved by the Tensor Memory Accelerator:
-//   * load : ONE cp.async.bulk.tensor.2d per tile (box 32 samples x 32 streams of x[S][T]),
-//            completion on an mbarrier (complete_tx), issued by lane 0;
-//   * store: ONE cp.async.bulk.tensor.3d per tile (box 32 samples x 1 channel x 32 streams of
-//            y[S][C][T]) straight from the same shared buffer.
-// The shared tile is dense [32 rows][128 B] with the hardware 128-byte swizzle (16-byte chunk
-// index XOR row & 7), so the per-lane row accesses (LDS.128 / STS.128, lane = row) are bank
-// conflict free without padding, and ragged edges (S % 32, T % 32) are handled by the TMA's
-// out-of-bounds zero fill / store clipping: no predicated copy loops, no address arithmetic
-// in the warp, ~150 instructions per tile less than the cp.async engine.
-// Requires 16-byte aligned base pointers and row strides (else the cp.async engine is used).
+// Same algorithm as alz_run_warp_tma (alz_lane_tma.cuh): every warp is an independent worker with
+// its own two tiles and mbarriers, there is no CTA barrier.  W > 1 only amortises the 1 KB of
+// shared memory the system reserves per CTA (W = 3: 9 CTAs x 3 warps = 27 warps per SM instead of
+// 24).  To fit the 72-register budget of 27 warps per SM the long-lived values are narrower here
+// (32-bit segment bounds, state index and flag address recomputed at the end): 66 registers, no
+// spills.  Selected with ALZ_WARPS_PER_CTA=3; NOT YET RUN ON HARDWARE.  Kept in a separate
+// function so that the measured single-warp engine keeps its exact code.
 #pragma once
-#include <cuda.h>
-#include "alz_lane.cuh"
+#include "alz_lane_tma.cuh"
 
-#define ALZ_TMA_TILE_BYTES 4096                      // 32 rows x 128 B
-#define ALZ_TMA_SMEM (2 * ALZ_TMA_TILE_BYTES + 16)   // two tiles + two mbarriers
-
-__device__ __forceinline__ unsigned alz_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void alz_mbar_init(unsigned mbar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void alz_mbar_expect_tx(unsigned mbar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void alz_mbar_wait(unsigned mbar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "ALZ_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra ALZ_DONE;\n"
-      "bra ALZ_WAIT;\n"
-      "ALZ_DONE:\n"
-      "}\n" ::"r"(mbar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void alz_tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, unsigned mbar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
-               ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void alz_tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, unsigned src) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\n"
-               ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
-}
-__device__ __forceinline__ void alz_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void alz_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-__device__ __forceinline__ void alz_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void alz_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-template <class Core, class CoreArgs>
-__device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const CoreArgs& ca, const CUtensorMap* tmx,
+// All warps of a CTA share the channel (blockIdx.x); warp w of CTA y takes stream group / ticket y*W + w.
+template <class Core, class CoreArgs, int W>
+__device__ __forceinline__ void alz_run_warps_tma_wide(const AlzTileArgs& a, const CoreArgs& ca, const CUtensorMap* tmx,
                                                  const CUtensorMap* tmy, unsigned char* smem) {
-  const int lane = threadIdx.x;
+  const int lane = W == 1 ? threadIdx.x : (threadIdx.x & 31);
+  const int warp = W == 1 ? 0 : (threadIdx.x >> 5);
   const int c_local = blockIdx.x;              // CTA-uniform: coefficients go to uniform registers
   const int c = a.c_base + c_local;
-  int group = blockIdx.y, seg = 0;
-  long long tbeg = 0, tlen = a.T;
+  int group = W == 1 ? blockIdx.y : blockIdx.y * W + warp, seg = 0;
+  int tbeg = 0, tlen = (int)a.T;
   unsigned* flag = nullptr;
+  if constexpr (W > 1) {
+    if (a.nseg <= 1 && group >= a.groups) return;   // surplus warp of the last CTA
+  }
   if (a.nseg > 1) {
     // Ticket order = start order within the channel, so the CTA that owns the previous segment
     // of my (channel, group) is already running or done: the wait below cannot deadlock.
     unsigned ticket = 0;
     if (lane == 0) ticket = atomicAdd(a.sync + c_local, 1u);
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if constexpr (W > 1) {
+      if (ticket >= (unsigned)a.groups * (unsigned)a.nseg) return;
+    }
     seg = (int)(ticket / (unsigned)a.groups);
     group = (int)(ticket - (unsigned)seg * (unsigned)a.groups);
-    tbeg = (long long)seg * a.seg_len;
-    tlen = a.T - tbeg < a.seg_len ? a.T - tbeg : a.seg_len;
+    tbeg = seg * (int)a.seg_len;
+    tlen = (int)a.T - tbeg < (int)a.seg_len ? (int)a.T - tbeg : (int)a.seg_len;
     flag = a.sync + gridDim.x + (size_t)c_local * a.groups + group;
     if (seg > 0) {
       unsigned done;
@@ -78,13 +45,15 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
       } while (done < (unsigned)seg);
     }
   }
-  const long long s0 = (long long)group * 32;
-  const long long s = s0 + lane;
+  const int s0 = group * 32;
+  const long long s = (long long)s0 + lane;
   const bool valid = s < a.S;
   const long long r = (long long)c * a.Stot + (valid ? s : a.S - 1);   // stream-fastest: coalesced state access
 
+  if constexpr (W > 1) smem += warp * (2 * ALZ_TMA_TILE_BYTES);   // tiles of all warps first (1024-byte aligned) ...
   const unsigned tile0 = alz_smem_u32(smem);
-  const unsigned mbar0 = tile0 + 2 * ALZ_TMA_TILE_BYTES;
+  const unsigned mbar0 = W == 1 ? tile0 + 2 * ALZ_TMA_TILE_BYTES                                   // ... mbarriers after them
+                                : tile0 + (W - warp) * (2 * ALZ_TMA_TILE_BYTES) + warp * 16;
   if (lane == 0) {
     alz_mbar_init(mbar0, 1);
     alz_mbar_init(mbar0 + 8, 1);
@@ -95,9 +64,9 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   Core core;
   core.load(ca, r, c_local, valid);
 
-  const int ntiles = (int)((tlen + ALZ_TT - 1) / ALZ_TT);
-  const int nfull = (int)(tlen / ALZ_TT);
-  const int tb = (int)tbeg;
+  const int ntiles = (tlen + ALZ_TT - 1) / ALZ_TT;
+  const int nfull = tlen / ALZ_TT;
+  const int tb = tbeg;
   const int swz = lane & 7;
   float* const myrow = reinterpret_cast<float*>(smem) + lane * 32;
 
@@ -160,8 +129,9 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
     for (int j = 0; j < nvalid; ++j) dst[j] = src[(((j >> 2) ^ swz) << 2) | (j & 3)];
   }
   if (lane == 0) alz_bulk_wait0();                   // all output tiles are globally written before exit
-  if (valid) core.store(ca, r, tlen);
-  if (flag != nullptr && seg + 1 < a.nseg) {         // hand the state to the next segment
+  if (valid) core.store(ca, (long long)c * a.Stot + ((long long)group * 32 + lane), tlen);
+  if (a.nseg > 1 && seg + 1 < a.nseg) {         // hand the state to the next segment
+    flag = a.sync + gridDim.x + (size_t)c_local * a.groups + group;
     __threadfence();
     __syncwarp();
     if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(flag), "r"((unsigned)(seg + 1)) : "memory");
