@@ -316,3 +316,30 @@ def test_row_padding_is_never_written(gpu, designs):
     torch.cuda.synchronize()
     assert bool(torch.isnan(ys[:, :, T:]).all()), (S, T)
     assert np.array_equal(ys[:, :, :T].cpu().numpy(), want), (S, T)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("ALZ_TEST_EXPERIMENTAL"), reason="experimental engine: set ALZ_TEST_EXPERIMENTAL=1")
+def test_experimental_wide_cta_engine(gpu, designs, monkeypatch):
+  """ALZ_WARPS_PER_CTA=3 (alz_lane_tma_wide.cuh) must reproduce the single-warp engine bit for bit:
+  plain, paired, time-segmented and ragged launches."""
+  torch = gpu.torch
+  cur = torch.cuda.current_stream().cuda_stream
+  for name in ["bank_slaney", "bank_klapuri"]:
+    plan = gpu.capi.Plan(designs[name])
+    for S, T in [(40, 500), (2048 + 5, 2048 + 76), (2048 + 5, 2048 + 77), (4096, 4096)]:
+      x = torch.rand((S, T), device=gpu.dev) * 2 - 1
+      stride = (T + 3) // 4 * 4
+      xs = torch.zeros((S, stride), device=gpu.dev)
+      xs[:, :T] = x
+      outs = []
+      for wide in ("1", "3"):
+        monkeypatch.setenv("ALZ_WARPS_PER_CTA", wide)
+        ys = torch.full((S, 64, stride), float("nan"), device=gpu.dev)
+        st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=gpu.dev)
+        plan.apply(xs.data_ptr(), ys.data_ptr(), st.data_ptr(), S, T, stride, stride, cur)
+        torch.cuda.synchronize()
+        outs.append((ys, st))
+      monkeypatch.delenv("ALZ_WARPS_PER_CTA")
+      assert torch.equal(outs[0][0][:, :, :T], outs[1][0][:, :, :T]), (name, S, T)
+      assert bool(torch.isnan(outs[1][0][:, :, T:]).all()), (name, S, T)
+      assert torch.equal(outs[0][1], outs[1][1]), (name, S, T)
