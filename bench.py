@@ -204,6 +204,7 @@ def run_ours(args):
   distributed = world > 1
   if distributed:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not mix with the JSON line on stdout
     dist.init_process_group("nccl", device_id=dev)
 
   S, Tn = args.streams, args.samples
