@@ -85,3 +85,17 @@ def test_missing_library_is_loud(monkeypatch):
   monkeypatch.setenv("ALZ_B200_LIB", "/nonexistent/libalz_b200.so")
   with pytest.raises(_capi.NativeError, match="no CPU fallback"):
     _capi.lib()
+
+
+def test_header_is_plain_c(tmp_path):
+  """include/alz_b200.h is the boundary: it must compile as C99 and as C++ on its own."""
+  import shutil
+  import subprocess
+  inc = os.path.join(ROOT, "include")
+  for compiler, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "cpp")):
+    if shutil.which(compiler) is None:
+      pytest.skip(compiler + " not available")
+    src = tmp_path / ("use_header." + ext)
+    src.write_text('#include "alz_b200.h"\nint main(void) { return ALZ_OK; }\n')
+    subprocess.run([compiler, std, "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(src)],
+                   check=True, capture_output=True)
