@@ -81,8 +81,8 @@ class DeviceBank(object):
     torch = torch_mod()
     if x.dim() == 1:
       x = x.unsqueeze(0)
-    if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 2:
-      raise ValueError("x must be a CUDA float32 tensor of shape [streams, samples]")
+    if x.dtype != torch.float32 or x.device != self.device or x.dim() != 2:
+      raise ValueError("x must be a float32 tensor [streams, samples] on the bank's CUDA device (%s)" % self.device)
     if x.stride(1) != 1:
       x = x.contiguous()
     S, T = x.shape
