@@ -73,3 +73,12 @@ def test_errors_raise_at_call_time(fake):
     broken([1.0])
   with pytest.raises(NotImplementedError):
     ab.ZFilter([1j, 1.0])([1.0, 2.0])           # complex coefficients have no accelerated path (and no fallback)
+
+
+def test_configs_through_the_python_api(fake, designs, vectors):
+  gpu_cases.test_configs_through_the_python_api(fake, designs, vectors)
+
+
+@pytest.mark.parametrize("strategy", ["slaney", "sampled"])
+def test_gammatone_channels_and_bank(fake, vectors, strategy):
+  gpu_cases.test_gammatone_channels_and_bank(fake, vectors, strategy)
