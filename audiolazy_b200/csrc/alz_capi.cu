@@ -627,7 +627,7 @@ int32_t alz_plan_history(const alz_plan* p, int32_t* xd, int32_t* yd) {
 }
 
 // Broadcast one per-channel row of slot values to all streams: state[slot*R + c*S + s].
-__global__ void alz_state_fill_kernel(double* state, const double* proto, long long R, int C, int slots) {
+static __global__ void alz_state_fill_kernel(double* state, const double* proto, long long R, int C, int slots) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * slots) return;
   const long long slot = i / R, r = i - slot * R, S = R / C;
@@ -707,7 +707,7 @@ static int apply_launch(const alz_plan* p, AlzTileArgs ta, double* state, long l
 //   pass 2  every chunk again, from its true initial state                        -> the output
 // Exact in exact arithmetic; in float64 the chunk states differ from the sequential ones by
 // rounding only (parity bar 1e-5; tests/test_gpu_parity.py::test_time_parallel_path).
-__global__ void alz_unit_state_kernel(double* m, int d, int C) {   // m[slot j][(c*d + i)] = (i == j)
+static __global__ void alz_unit_state_kernel(double* m, int d, int C) {   // m[slot j][(c*d + i)] = (i == j)
   const long long n = (long long)d * d * C;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -717,7 +717,7 @@ __global__ void alz_unit_state_kernel(double* m, int d, int C) {   // m[slot j][
 
 // One WARP per channel (d <= 32): lane j owns state slot j, keeps row j of M in registers and
 // the running state is exchanged with shuffles; F of the next chunk is prefetched.
-__global__ void __launch_bounds__(32) alz_chunk_scan_kernel(const double* __restrict__ F, double* __restrict__ init,
+static __global__ void __launch_bounds__(32) alz_chunk_scan_kernel(const double* __restrict__ F, double* __restrict__ init,
                                                             const double* __restrict__ M, double* user_state,
                                                             long long user_stride, long long user_stot, int d, int C,
                                                             long long P) {
@@ -958,7 +958,7 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
   return rc;
 }
 
-__global__ void alz_sum_channels_kernel(const float* y, float* out, long long S, int C, long long T, long long ys,
+static __global__ void alz_sum_channels_kernel(const float* y, float* out, long long S, int C, long long T, long long ys,
                                         long long os) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S * T) return;
@@ -983,7 +983,7 @@ int32_t alz_sum_channels_f32(const float* y, float* out, int64_t S, int32_t C, i
 
 // H_c(e^{jw}) = prod_k B_ck(z^-1) / A_ck(z^-1) at z^-1 = e^{-jw}: one thread per (channel, frequency),
 // Horner in complex float64 (reference lazy_filters.py:267-301 evaluates numpoly / denpoly the same way).
-__global__ void alz_freq_response_kernel(const double* __restrict__ coef, const int* __restrict__ desc, int C, int K,
+static __global__ void alz_freq_response_kernel(const double* __restrict__ coef, const int* __restrict__ desc, int C, int K,
                                          const double* __restrict__ w, long long n, double* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;

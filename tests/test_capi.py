@@ -29,6 +29,12 @@ def test_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(lib, name), "library does not export %s" % name
   assert sorted(_capi.SYMBOLS) == declared           # the Python binding covers the whole ABI
+  import shutil
+  import subprocess
+  if shutil.which("nm"):                             # ... and nothing else with the prefix leaks out of the library
+    out = subprocess.run(["nm", "-D", "--defined-only", _build.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(line.split()[-1] for line in out.splitlines() if " T alz_" in line)
+    assert exported == declared
   assert _capi.lib().alz_abi_version() == 1
 
 
