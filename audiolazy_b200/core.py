@@ -76,8 +76,23 @@ class StrategyDict(object):
   def __len__(self):
     return len(self._unique)
 
+  # -- the dictionary view of the reference's MultiKeyDict: one entry per strategy, keyed by the tuple of its names
+  def value2keys(self, func):
+    """All names of a strategy, in registration order (``()`` when it is not one)."""
+    return tuple(name for name, value in self._names.items() if value is func)
+
+  def key2keys(self, name):
+    """All names of the strategy that ``name`` designates."""
+    return self.value2keys(self._names[name]) if name in self._names else ()
+
   def keys(self):
-    return list(self._names)
+    return [self.value2keys(func) for func in self._unique]
+
+  def values(self):
+    return list(self._unique)
+
+  def items(self):
+    return [(self.value2keys(func), func) for func in self._unique]
 
   def __repr__(self):
     return "<StrategyDict %s: %s>" % (self.__name__, ", ".join(f.__name__ for f in self._unique))

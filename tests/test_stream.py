@@ -68,3 +68,16 @@ def test_poly():
     (x ** -3 + 4).order
   with pytest.raises(NotImplementedError):
     (x + 1) / (x + 2)
+
+
+def test_strategy_dict_dictionary_views():
+  """keys / items / values / key2keys / value2keys as the reference's MultiKeyDict gives them:
+  one entry per strategy, keyed by the tuple of all its names (lazy_core.py:431-659)."""
+  from audiolazy_b200 import erb, lowpass, gammatone
+  assert erb.keys() == [("gm90", "glasberg_moore_90", "glasberg_moore"), ("mg83", "moore_glasberg_83")]
+  assert [(k, f.__name__) for k, f in erb.items()] == [(erb.keys()[0], "gm90"), (erb.keys()[1], "mg83")]
+  assert erb.values() == [erb.gm90, erb.mg83] and list(erb) == erb.values()
+  assert erb.key2keys("moore_glasberg_83") == ("mg83", "moore_glasberg_83") and erb.key2keys("nope") == ()
+  assert erb.value2keys(erb.gm90) == erb.keys()[0]
+  assert [k[0] for k in gammatone.keys()] == ["sampled", "slaney", "klapuri"]
+  assert lowpass.default is lowpass.pole and len(lowpass) == 4
