@@ -23,11 +23,13 @@ ALZ_ERR_UNSUPPORTED = -6
 KIND_BIQUAD = 1
 KIND_GENERIC = 2
 PLAN_FORCE_GENERIC = 1
+PLAN_EXACT = 2
+PLAN_DESIGN_ONLY = 4
 
 #: every symbol include/alz_b200.h declares (tests check the library exports them all)
 SYMBOLS = (
   "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_create_ex",
-  "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32",
+  "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32", "alz_plan_tiers",
   "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
   "alz_apply_f32_host", "alz_sum_channels_f32", "alz_freq_response_f64", "alz_launch_count",
 )
@@ -40,7 +42,7 @@ class NativeError(RuntimeError):
 class PlanInfo(ctypes.Structure):
   _fields_ = [(n, ctypes.c_int32) for n in
               ("abi_version", "kind", "n_channels", "n_sections", "num_taps", "monic", "state_doubles", "fp64_ops",
-               "device")] + [("reserved", ctypes.c_int32 * 7)]
+               "device", "n_fp32_channels", "tier_tol_e9")] + [("reserved", ctypes.c_int32 * 5)]
 
 
 _lib = None
@@ -73,6 +75,8 @@ def lib():
   L.alz_plan_create_ex.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp)]
   L.alz_plan_taps.restype = i32
   L.alz_plan_taps.argtypes = [vp, vp, vp, i32]
+  L.alz_plan_tiers.restype = i32
+  L.alz_plan_tiers.argtypes = [vp, vp, vp, i32]
   L.alz_apply_tv_f32.restype = i32
   L.alz_apply_tv_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp, i64, vp]
   L.alz_plan_destroy.restype = None
@@ -129,12 +133,13 @@ def pack_sections(bank):
 class Plan(object):
   """A compiled bank of cascades living on the current CUDA device."""
 
-  def __init__(self, bank, force_generic=False):
+  def __init__(self, bank, force_generic=False, exact=False, design_only=False):
     L = lib()
     coef, desc, C, KM = pack_sections(bank)
     handle = ctypes.c_void_p()
-    _check(L.alz_plan_create_ex(coef.ctypes.data, desc.ctypes.data, C, KM, PLAN_FORCE_GENERIC if force_generic else 0,
-                                ctypes.byref(handle)))
+    flags = (PLAN_FORCE_GENERIC if force_generic else 0) | (PLAN_EXACT if exact else 0) | \
+            (PLAN_DESIGN_ONLY if design_only else 0)
+    _check(L.alz_plan_create_ex(coef.ctypes.data, desc.ctypes.data, C, KM, flags, ctypes.byref(handle)))
     self._h = handle
     info = PlanInfo()
     _check(L.alz_plan_info_get(self._h, ctypes.byref(info)))
@@ -146,6 +151,8 @@ class Plan(object):
     self.state_doubles_per_recurrence = info.state_doubles
     self.fp64_ops = info.fp64_ops
     self.device = info.device
+    self.n_fp32_channels = info.n_fp32_channels
+    self.tier_tol = info.tier_tol_e9 * 1e-9
     xd, yd = ctypes.c_int32(), ctypes.c_int32()
     _check(L.alz_plan_history(self._h, ctypes.byref(xd), ctypes.byref(yd)))
     self.xd, self.yd = xd.value, yd.value
@@ -171,6 +178,14 @@ class Plan(object):
   def apply(self, x_ptr, y_ptr, state_ptr, n_streams, n_samples, x_stride, y_stride, stream=0):
     _check(lib().alz_apply_f32(self._h, x_ptr, y_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),
                                int(y_stride), stream))
+
+  def tiers(self):
+    """``(tier int32[C], probe_err float64[C])``: precision tier of every channel (0 float64, 1 float32) and the
+    float32 error the plan-time probe measured for it (< 0: not probed)."""
+    tier = np.zeros(self.n_channels, dtype=np.int32)
+    err = np.zeros(self.n_channels, dtype=np.float64)
+    _check(lib().alz_plan_tiers(self._h, tier.ctypes.data, err.ctypes.data, self.n_channels))
+    return tier, err
 
   def taps(self):
     """``[(delay, is_den), ...]`` in coefficient-table order (generic plans only)."""

@@ -41,22 +41,38 @@
 #endif
 constexpr int kAlzGroupUnroll = ALZ_GROUP_UNROLL;
 
-// Per-channel coefficient record inside the kernel parameters (constant bank):
+// Per-POSITION coefficient record inside the kernel parameters (constant bank); position =
+// blockIdx.x of the launch, the plan orders channels so that precision tiers interleave:
 //   [k*5 + 0..4] = b0 (1 when monic), b1|c1, b2|c2, -a1, -a2   (all / a0);  [5K] = G;
-//   head-FIR plans (NB0 = 8): [5K+1 .. 5K+5] = taps 3..7 of the FIRST section.
-#define ALZ_COEF_STRIDE(K, NB0) (5 * (K) + 1 + ((NB0) > 3 ? (NB0) - 3 : 0))
+//   head-FIR plans (NB0 = 8): [5K+1 .. 5K+5] = taps 3..7 of the FIRST section;
+//   last slot (ALZ_COEF_META) = channel index + 65536 * tier, as a double.
+// Tier 0 records hold doubles; tier 1 (float32 recurrence) records hold the SAME entries as
+// floats packed from the start of the record (entry i at float index i).
+#define ALZ_COEF_NVAL(K, NB0) (5 * (K) + 1 + ((NB0) > 3 ? (NB0) - 3 : 0))
+#define ALZ_COEF_STRIDE(K, NB0) (ALZ_COEF_NVAL(K, NB0) + 1)
+#define ALZ_COEF_META(K, NB0) ALZ_COEF_NVAL(K, NB0)
 // State: state[slot * sstride + r], r = c*Stot + s (working units; consecutive lanes = consecutive
 // streams touch consecutive doubles).  Section 0: H0 input
 // delays (H0 = max(NB0 - 1, 2)) then yd1, yd2; section k >= 1: xd1, xd2, yd1, yd2.
 #define ALZ_H0(NB0) ((NB0) > 3 ? (NB0) - 1 : 2)
 #define ALZ_STATE_BASE(k, NB0) ((k) == 0 ? 0 : ALZ_H0(NB0) + 2 + 4 * ((k) - 1))
 #define ALZ_STATE_SLOTS(K, NB0) (ALZ_H0(NB0) + 2 + 4 * ((K) - 1))
+// Built ONCE per plan (one block per launch chunk) and handed to cudaLaunchKernel by address: no
+// per-launch copy on the host, no lock, any number of host threads / devices.
 template <int NCOEF>
 struct AlzBiquadArgs {
-  double* state;
-  long long sstride;   // slot stride of the state buffer (recurrences it was sized for)
-  double coef[NCOEF];  // [channels of this launch][ALZ_COEF_STRIDE(K)]
+  int rec_stride;      // ALZ_COEF_STRIDE of the plan
+  int n_pos;           // positions (channels) of this launch chunk
+  double coef[NCOEF];  // [positions of this launch][rec_stride]
+  __device__ __forceinline__ int meta(int pos) const { return (int)coef[pos * rec_stride + rec_stride - 1]; }
+  __device__ __forceinline__ int channel(int pos) const { return meta(pos) & 0xffff; }
+  __device__ __forceinline__ int tier(int pos) const { return meta(pos) >> 16; }
 };
+
+// fused multiply-add in the working type (host versions: the plan-time tier probe runs the
+// SAME arithmetic on the CPU, fma/fmaf are correctly rounded there too)
+__host__ __device__ __forceinline__ double alz_fma(double a, double b, double c) { return fma(a, b, c); }
+__host__ __device__ __forceinline__ float alz_fma(float a, float b, float c) { return fmaf(a, b, c); }
 
 // MONIC: 0 = plain sections; 1 = b0 factored out, gain applied to the float64 OUTPUT (one
 // DMUL per sample, bit-faithful); 2 = b0 factored out, gain applied to the float32 INPUT
@@ -68,21 +84,26 @@ struct AlzBiquadArgs {
 // reference's Poly drops zero coefficients too): bit 2k = tap 1 of section k, bit 2k+1 = tap 2.
 // ALZ_ZMASK_KLAPURI is gammatone.klapuri's cascade [1 - z^-2, const, 1 - z^-2, const] / poles.
 #define ALZ_ZMASK_KLAPURI 0xDD
-template <int K, int NB, int MONIC, int NB0 = 0, int ZMASK = 0>
+// W: working type of the recurrence.  double = tier 0 (every channel qualifies); float = tier 1,
+// only for channels whose float32 evaluation was MEASURED at plan creation to stay well inside
+// the parity bar (alz_capi.cu: tier probe) -- high ERB channels with poles far from z = 1.  The
+// float32 warps use the FP32 pipe and no conversions, and run in the issue slots the FP64 warps
+// of the same SM leave free.
+template <int K, int NB, int MONIC, int NB0 = 0, int ZMASK = 0, typename W = double>
 struct AlzBiquadCore {
   static constexpr int H0 = ALZ_H0(NB0);
   static constexpr int NBF = NB0 > 3 ? NB0 : NB;   // taps of section 0
-  double b0[K], c1[K], c2[K], na1[K], na2[K];
-  double ch[NB0 > 3 ? NB0 - 3 : 1];                // taps 3.. of section 0
-  double G;
+  W b0[K], c1[K], c2[K], na1[K], na2[K];
+  W ch[NB0 > 3 ? NB0 - 3 : 1];                // taps 3.. of section 0
+  W G;
   float Gf;
-  double u[K + 1][2];   // u[k][0] = u_k[n-1], u[k][1] = u_k[n-2]; u[0] = input history (NB0 <= 3)
-  double xh[H0];        // input history of section 0 when NB0 > 3 (xh[j] = x[n-1-j])
-  double xe[K][2];      // explicit input histories of sections 1..K-1 (index 0 unused)
+  W u[K + 1][2];   // u[k][0] = u_k[n-1], u[k][1] = u_k[n-2]; u[0] = input history (NB0 <= 3)
+  W xh[H0];        // input history of section 0 when NB0 > 3 (xh[j] = x[n-1-j])
+  W xe[K][2];      // explicit input histories of sections 1..K-1 (index 0 unused)
 
-  template <class Args>
-  __device__ __forceinline__ void load(const Args& ca, long long r, int c_local, bool /*valid*/) {
-    const double* cf = ca.coef + c_local * ALZ_COEF_STRIDE(K, NB0);   // CTA-uniform address
+  // coefficient record -> registers (rec: this position's record; doubles for W = double, packed floats for float)
+  __host__ __device__ __forceinline__ void load_coef(const double* rec) {
+    const W* cf = reinterpret_cast<const W*>(rec);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       b0[k] = cf[5 * k + 0];
@@ -97,54 +118,69 @@ struct AlzBiquadCore {
 #pragma unroll
       for (int j = 3; j < NB0; ++j) ch[j - 3] = cf[5 * K + 1 + (j - 3)];
     }
-    const double* st = ca.state + r;
-    const long long R = ca.sstride;
+  }
+  __host__ __device__ __forceinline__ void zero_state() {
 #pragma unroll
-    for (int j = 0; j < H0; ++j) xh[j] = __ldcg(st + (long long)j * R);   // .cg: the state may have been written by another CTA of this launch
+    for (int j = 0; j < H0; ++j) xh[j] = W(0);
+#pragma unroll
+    for (int k = 0; k <= K; ++k) u[k][0] = u[k][1] = W(0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) xe[k][0] = xe[k][1] = W(0);
+  }
+
+  // The state buffer always holds float64 working-unit values; a float32 tier narrows on load and
+  // widens (exactly) on store, so block splitting stays bit-exact in either tier.
+  template <class Args>
+  __device__ __forceinline__ void load(const AlzTileArgs& a, const Args& ca, long long r, int c_local, bool /*valid*/) {
+    load_coef(ca.coef + c_local * ALZ_COEF_STRIDE(K, NB0));   // CTA-uniform address
+    const double* st = a.state + r;
+    const long long R = a.sstride;
+#pragma unroll
+    for (int j = 0; j < H0; ++j) xh[j] = (W)__ldcg(st + (long long)j * R);   // .cg: the state may have been written by another CTA of this launch
     u[0][0] = xh[0]; u[0][1] = xh[1];
-    xe[0][0] = xe[0][1] = 0.0;
-    u[1][0] = __ldcg(st + (long long)(H0 + 0) * R);
-    u[1][1] = __ldcg(st + (long long)(H0 + 1) * R);
+    xe[0][0] = xe[0][1] = W(0);
+    u[1][0] = (W)__ldcg(st + (long long)(H0 + 0) * R);
+    u[1][1] = (W)__ldcg(st + (long long)(H0 + 1) * R);
 #pragma unroll
     for (int k = 1; k < K; ++k) {
       const int base = ALZ_STATE_BASE(k, NB0);
-      xe[k][0] = __ldcg(st + (long long)(base + 0) * R);
-      xe[k][1] = __ldcg(st + (long long)(base + 1) * R);
-      u[k + 1][0] = __ldcg(st + (long long)(base + 2) * R);
-      u[k + 1][1] = __ldcg(st + (long long)(base + 3) * R);
+      xe[k][0] = (W)__ldcg(st + (long long)(base + 0) * R);
+      xe[k][1] = (W)__ldcg(st + (long long)(base + 1) * R);
+      u[k + 1][0] = (W)__ldcg(st + (long long)(base + 2) * R);
+      u[k + 1][1] = (W)__ldcg(st + (long long)(base + 3) * R);
     }
   }
 
   // Section 0 with a head FIR: reads and shifts the input history xh.
-  __device__ __forceinline__ double head(double in) {
-    double t = MONIC ? in : b0[0] * in;
-    t = fma(c1[0], xh[0], t);
-    t = fma(c2[0], xh[1], t);
+  __host__ __device__ __forceinline__ W head(W in) {
+    W t = MONIC ? in : b0[0] * in;
+    t = alz_fma(c1[0], xh[0], t);
+    t = alz_fma(c2[0], xh[1], t);
 #pragma unroll
-    for (int j = 3; j < NB0; ++j) t = fma(ch[j - 3], xh[j - 1], t);
+    for (int j = 3; j < NB0; ++j) t = alz_fma(ch[j - 3], xh[j - 1], t);
 #pragma unroll
     for (int j = H0 - 1; j > 0; --j) xh[j] = xh[j - 1];
     xh[0] = in;
-    const double y1 = u[1][0], y2 = u[1][1];
-    t = fma(na2[0], y2, t);
-    const double y = fma(na1[0], y1, t);
+    const W y1 = u[1][0], y2 = u[1][1];
+    t = alz_fma(na2[0], y2, t);
+    const W y = alz_fma(na1[0], y1, t);
     u[1][1] = y1;
     u[1][0] = y;
     return y;
   }
 
   // One section's arithmetic.  in/in1/in2 = u_{k-1}[n], [n-1], [n-2].
-  __device__ __forceinline__ double section(int k, double in, double in1, double in2, double y1, double y2) const {
-    double t = MONIC ? in : b0[k] * in;
-    if (NB >= 2 && !((ZMASK >> (2 * k)) & 1)) t = fma(c1[k], in1, t);
-    if (NB >= 3 && !((ZMASK >> (2 * k + 1)) & 1)) t = fma(c2[k], in2, t);
-    t = fma(na2[k], y2, t);
-    return fma(na1[k], y1, t);
+  __host__ __device__ __forceinline__ W section(int k, W in, W in1, W in2, W y1, W y2) const {
+    W t = MONIC ? in : b0[k] * in;
+    if (NB >= 2 && !((ZMASK >> (2 * k)) & 1)) t = alz_fma(c1[k], in1, t);
+    if (NB >= 3 && !((ZMASK >> (2 * k + 1)) & 1)) t = alz_fma(c2[k], in2, t);
+    t = alz_fma(na2[k], y2, t);
+    return alz_fma(na1[k], y1, t);
   }
 
   // Steady state: section k reads the history of section k-1's output.
-  __device__ __forceinline__ float step_alias(double xin) {
-    double in = xin, in1, in2;
+  __host__ __device__ __forceinline__ float step_alias(W xin) {
+    W in = xin, in1, in2;
     if (NB0 > 3) {
       in1 = u[1][0]; in2 = u[1][1];       // section 1 reads section 0's OLD output history
       in = head(xin);
@@ -155,8 +191,8 @@ struct AlzBiquadCore {
     }
 #pragma unroll
     for (int k = (NB0 > 3 ? 1 : 0); k < K; ++k) {
-      const double y1 = u[k + 1][0], y2 = u[k + 1][1];
-      const double y = section(k, in, in1, in2, y1, y2);
+      const W y1 = u[k + 1][0], y2 = u[k + 1][1];
+      const W y = section(k, in, in1, in2, y1, y2);
       u[k + 1][1] = y1;
       u[k + 1][0] = y;
       in = y; in1 = y1; in2 = y2;
@@ -165,16 +201,16 @@ struct AlzBiquadCore {
   }
 
   // First two samples of a launch: explicit input histories.
-  __device__ __forceinline__ float step_explicit(double xin) {
-    double in = xin;
+  __host__ __device__ __forceinline__ float step_explicit(W xin) {
+    W in = xin;
     if (NB0 > 3) in = head(xin);
 #pragma unroll
     for (int k = (NB0 > 3 ? 1 : 0); k < K; ++k) {
-      double in1, in2;
+      W in1, in2;
       if (k == 0) { in1 = u[0][0]; in2 = u[0][1]; u[0][1] = in1; u[0][0] = in; }
       else { in1 = xe[k][0]; in2 = xe[k][1]; xe[k][1] = in1; xe[k][0] = in; }
-      const double y1 = u[k + 1][0], y2 = u[k + 1][1];
-      const double y = section(k, in, in1, in2, y1, y2);
+      const W y1 = u[k + 1][0], y2 = u[k + 1][1];
+      const W y = section(k, in, in1, in2, y1, y2);
       u[k + 1][1] = y1;
       u[k + 1][0] = y;
       in = y;
@@ -185,7 +221,7 @@ struct AlzBiquadCore {
   // float32 sample -> float64 section input (with the input-side gain when MONIC == 2)
   // (Widening normal numbers with integer instructions instead of F2F.F64.F32 -- exponent re-bias +
   // mantissa shift, conversion unit only for zero/denormal/inf/NaN -- was measured SLOWER: 4.31 vs 3.92 ms.)
-  __device__ __forceinline__ double widen(float x) const { return MONIC == 2 ? (double)(x * Gf) : (double)x; }
+  __host__ __device__ __forceinline__ W widen(float x) const { return MONIC == 2 ? (W)(x * Gf) : (W)x; }
 
   // Filter my row of the tile in place: float32 in, float32 out.  `swz` is the XOR
   // applied to the 16-byte chunk index (0 for the padded cp.async tile, lane & 7 for the
@@ -225,35 +261,34 @@ struct AlzBiquadCore {
     } else {
       for (int j = 0; j < nvalid; ++j) {
         float* p = row + ((((j >> 2) ^ swz) << 2) | (j & 3));
-        const double xin = widen(*p);
+        const W xin = widen(*p);
         *p = (n_done + j < 2) ? step_explicit(xin) : step_alias(xin);
       }
     }
   }
 
-  template <class Args>
-  __device__ __forceinline__ void store(const Args& ca, long long r, long long T) {
-    double* st = ca.state + r;
-    const long long R = ca.sstride;
+  __device__ __forceinline__ void store(const AlzTileArgs& a, long long r, long long T) {
+    double* st = a.state + r;
+    const long long R = a.sstride;
     if (NB0 > 3) {
 #pragma unroll
-      for (int j = 0; j < H0; ++j) st[(long long)j * R] = xh[j];
+      for (int j = 0; j < H0; ++j) st[(long long)j * R] = (double)xh[j];
     } else {
-      st[0] = u[0][0];
-      st[R] = u[0][1];
+      st[0] = (double)u[0][0];
+      st[R] = (double)u[0][1];
     }
-    st[(long long)(H0 + 0) * R] = u[1][0];
-    st[(long long)(H0 + 1) * R] = u[1][1];
+    st[(long long)(H0 + 0) * R] = (double)u[1][0];
+    st[(long long)(H0 + 1) * R] = (double)u[1][1];
 #pragma unroll
     for (int k = 1; k < K; ++k) {
       const int base = ALZ_STATE_BASE(k, NB0);
-      double x1, x2;
+      W x1, x2;
       if (T >= 2) { x1 = u[k][0]; x2 = u[k][1]; }   // aliased: section k-1's output history
       else { x1 = xe[k][0]; x2 = xe[k][1]; }
-      st[(long long)(base + 0) * R] = x1;
-      st[(long long)(base + 1) * R] = x2;
-      st[(long long)(base + 2) * R] = u[k + 1][0];
-      st[(long long)(base + 3) * R] = u[k + 1][1];
+      st[(long long)(base + 0) * R] = (double)x1;
+      st[(long long)(base + 1) * R] = (double)x2;
+      st[(long long)(base + 2) * R] = (double)u[k + 1][0];
+      st[(long long)(base + 3) * R] = (double)u[k + 1][1];
     }
   }
 };

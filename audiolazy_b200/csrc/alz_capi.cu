@@ -1,29 +1,27 @@
 // alz_capi.cu -- the C ABI of include/alz_b200.h: plan building, state seeding,
 // kernel dispatch and the host-buffer pipeline.  No torch types, no CPU compute path.
+#pragma GCC visibility push(default)
 #include "../../include/alz_b200.h"
+#pragma GCC visibility pop
 #include "alz_biquad.cuh"
 #include "alz_generic.cuh"
 #include "alz_lane_tma.cuh"
-#include "alz_lane_tma_wide.cuh"
+#include "alz_plan.h"
 
 #include <algorithm>
-#include <atomic>
-#include <cstdarg>
 #include <cmath>
-#include <cstdio>
-#include <cstdlib>
 #include <cstring>
-#include <mutex>
-#include <string>
-#include <vector>
+
+static_assert(ALZI_OK == ALZ_OK && ALZI_ERR_CUDA == ALZ_ERR_CUDA && ALZI_ERR_UNSUPPORTED == ALZ_ERR_UNSUPPORTED, "status codes");
 
 // ----------------------------------------------------------------------------------
 // error plumbing
 // ----------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static std::atomic<long long> g_launches{0};
+std::atomic<long long> alzi_launches{0};
+#define g_launches alzi_launches
 
-static int fail(int code, const char* fmt, ...) {
+int alzi_fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -32,58 +30,21 @@ static int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
-#define ALZ_CUDA(expr)                                                                        \
-  do {                                                                                        \
-    cudaError_t e__ = (expr);                                                                 \
-    if (e__ != cudaSuccess)                                                                   \
-      return fail(ALZ_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-  } while (0)
+#define fail alzi_fail
 
-// ----------------------------------------------------------------------------------
-// plan
-// ----------------------------------------------------------------------------------
-struct HostPipe {   // lazily created resources of alz_apply_f32_host
-  static const int NBUF = 3;
-  cudaStream_t stream[NBUF] = {nullptr, nullptr, nullptr};
-  float* dx[NBUF] = {nullptr, nullptr, nullptr};
-  float* dy[NBUF] = {nullptr, nullptr, nullptr};
-  size_t dx_bytes = 0, dy_bytes = 0;
-  bool ready = false;
-};
-
-struct alz_plan {
-  int kind = 0, C = 0, K = 0, NB = 0, NB0 = 0, monic = 0, device = 0, sm_count = 148;
-  int zmask = 0;               // biquad: numerator taps that are zero in every channel (AlzBiquadCore ZMASK)
-  int xd = 0, yd = 0;          // history depths exposed to alz_state_init
-  int state_doubles = 0;       // per recurrence
-  int fp64_ops = 0;
-  // device tables
-  double* d_coef = nullptr;
-  AlzGenSection* d_sec = nullptr;
-  int* d_tap_delay = nullptr;
-  // host copies used by alz_state_init
-  std::vector<double> h_tab;              // biquad: [C][5K+1] coefficient records (kernel parameters)
-  std::vector<double> sc;                 // biquad: [C][K+1] working-unit scales
-  std::vector<AlzGenSection> h_sec;       // generic
-  std::vector<int> h_xlen, h_ylen;        // generic: true max delays per section
-  std::vector<int> h_tap_delay, h_tap_is_den;   // generic: tap order of the coefficient table
-  // normalised sections as given (a0 == 1), for alz_freq_response_f64
-  std::vector<double> fr_coef;            // b then a of every (channel, section), concatenated
-  std::vector<int> fr_desc;               // [C][K][3] = nb, na, offset (nb == 0: absent)
-  double* d_fr_coef = nullptr;
-  int fr_K = 0;
-  int* d_fr_desc = nullptr;
-  std::mutex host_mu;
-  HostPipe pipe;
-};
-
-static int env_int(const char* name, int dflt) {
+int alzi_env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
 }
+#define env_int alzi_env_int
+
+static double env_double(const char* name, double dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atof(v) : dflt;
+}
 
 // Keep the stream-ordered pool's memory across calls (its default trims at every sync).
-static void keep_async_pool() {
+void alzi_keep_async_pool() {
   static std::once_flag once[64];
   int dev = 0;
   cudaGetDevice(&dev);
@@ -96,44 +57,14 @@ static void keep_async_pool() {
     cudaGetLastError();
   });
 }
+#define keep_async_pool alzi_keep_async_pool
 
-// Kernel-parameter coefficient capacity (doubles).  CUDA 12.1+ allows 32764 bytes of
-// parameters; two sizes so that small filters do not push 28 KB per launch.
-static const int kCoefSmall = 512, kCoefLarge = 3584;
-static const int kWarpsPerSm = 22;   // 2 x 4608 B tile buffers + 1 KB CTA reserve -> 22 CTAs per SM
-
-template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
-__global__ void __launch_bounds__(32, kWarpsPerSm)
-alz_biquad_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca) {
-  extern __shared__ __align__(16) float alz_smem[];
-  alz_run_warp<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>>(a, ca, alz_smem);
-}
+static const int kCoefSmall = 512, kCoefLarge = 3584;   // as in alz_launch.cuh
 
 __global__ void __launch_bounds__(32)
 alz_generic_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzGenericArgs ca) {
   extern __shared__ __align__(16) float alz_smem[];
   alz_run_warp<AlzGenericCore>(a, ca, alz_smem);
-}
-
-// TMA variants: same cores, tiles moved by cp.async.bulk.tensor (16-byte aligned rows only).
-static const int kWarpsPerSmTma = 24;
-template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
-__global__ void __launch_bounds__(32, kWarpsPerSmTma)
-alz_biquad_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
-                      const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
-  extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
-  alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>>(a, ca, &tmx, &tmy, alz_smem_tma);
-}
-
-// EXPERIMENTAL (ALZ_WARPS_PER_CTA=3): three independent warps per CTA, same channel, consecutive stream
-// groups / tickets: 9 CTAs x 3 warps = 27 warps per SM instead of 24 (one 1 KB reserve per 3 warps).
-static const int kWarpsPerCtaWide = 3;
-template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
-__global__ void __launch_bounds__(32 * kWarpsPerCtaWide, 9)
-alz_biquad_tma_wide_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
-                           const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
-  extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
-  alz_run_warps_tma_wide<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK>, AlzBiquadArgs<NCOEF>, kWarpsPerCtaWide>(a, ca, &tmx, &tmy, alz_smem_tma);
 }
 
 __global__ void __launch_bounds__(32)
@@ -149,21 +80,20 @@ typedef CUresult (*alz_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static alz_encode_tiled_fn get_encode_tiled() {
   static alz_encode_tiled_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
       fn = (alz_encode_tiled_fn)p;
     cudaGetLastError();
-  }
+  });
   return fn;
 }
 
 // x[S][T] (row stride xs) and y[S][C][T] (row stride ys) as tiled tensor maps with 32-sample boxes.
-static bool make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap* tmy) {
+bool alzi_make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap* tmy) {
   alz_encode_tiled_fn enc = get_encode_tiled();
   if (!enc || !ta.vec_in || !ta.vec_out || env_int("ALZ_NO_TMA", 0)) return false;
   if (ta.T >= (1ll << 31) || ta.S >= (1ll << 31)) return false;
@@ -189,136 +119,41 @@ static bool make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMa
   return true;
 }
 
-// One launch: channels [c0, c0+nch) x stream groups of `ta` (ta.S <= 65535*32 streams).
-template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
-static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, int c0, int nch,
-                               cudaStream_t st) {
-  static AlzBiquadArgs<NCOEF> ca;   // too large for the stack of some callers; filled under a lock
-  static std::mutex mu;
-  std::lock_guard<std::mutex> lock(mu);
-  ca.state = state;
-  ca.sstride = sstride;
-  const int stride = ALZ_COEF_STRIDE(K, NB0);
-  memcpy(ca.coef, p->h_tab.data() + (size_t)c0 * stride, (size_t)nch * stride * sizeof(double));
-  ta.c_base = c0;
-  const long long groups = (ta.S + 31) / 32;
-  CUtensorMap tmx, tmy;
-  if (make_tensor_maps(ta, &tmx, &tmy)) {
-    // A launch of only a few waves of warps loses its last, partly filled wave: cut time into
-    // segments chained through the state (alz_lane.cuh) so the next segment fills the tail.
-    const long long warps = (long long)nch * groups, slots = (long long)p->sm_count * kWarpsPerSmTma;
-    ta.paired = env_int("ALZ_TMA_PAIRED", warps >= slots ? 1 : 0);
-    long long nseg = 1;
-    if (warps > slots && warps < 8 * slots && ta.T >= 2048 && !env_int("ALZ_NO_SEGMENT", 0)) {
-      const long long waves = std::max(1, env_int("ALZ_SEG_WAVES", 16)), min_len = std::max(32, env_int("ALZ_SEG_MIN", 1024));
-      nseg = std::min((waves * slots + warps - 1) / warps, ta.T / min_len);
-      const long long len = ((ta.T + nseg - 1) / nseg + 31) / 32 * 32;
-      nseg = (ta.T + len - 1) / len;
-      if (nseg > 1 && groups * nseg <= 65535) {
-        const size_t words = (size_t)nch + (size_t)nch * groups;
-        unsigned* sync = nullptr;
-        keep_async_pool();
-        ALZ_CUDA(cudaMallocAsync(&sync, words * 4, st));
-        if (cudaMemsetAsync(sync, 0, words * 4, st) != cudaSuccess) {
-          cudaFreeAsync(sync, st);
-          ALZ_CUDA(cudaGetLastError());
-        }
-        ta.nseg = (int)nseg; ta.groups = (int)groups; ta.seg_len = len; ta.sync = sync;
-      } else {
-        nseg = 1;
-      }
-    }
-    ta.groups = (int)groups;
-    bool wide = false;
-    // only the instantiations that fit 72 registers without spills (gammatone banks in gain mode 2)
-    constexpr bool kHasWide = K == 4 && NB0 == 0 && NCOEF == kCoefLarge && MONIC == 2 && (NB <= 2 || ZMASK != 0);
-    if constexpr (kHasWide) wide = env_int("ALZ_WARPS_PER_CTA", 1) == kWarpsPerCtaWide;
-    if (wide) {
-      if constexpr (kHasWide) {
-        const unsigned gy = (unsigned)((groups * nseg + kWarpsPerCtaWide - 1) / kWarpsPerCtaWide);
-        const size_t smem = (size_t)kWarpsPerCtaWide * (2 * ALZ_TMA_TILE_BYTES + 16);
-        static std::once_flag attr;
-        std::call_once(attr, [smem] {
-          cudaFuncSetAttribute(alz_biquad_tma_wide_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        });
-        alz_biquad_tma_wide_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, gy), 32 * kWarpsPerCtaWide, smem, st>>>(ta, ca, tmx, tmy);
-      }
-    } else {
-      alz_biquad_tma_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, (unsigned)(groups * nseg)), 32, ALZ_TMA_SMEM, st>>>(ta, ca, tmx, tmy);
-    }
-    if (ta.sync) cudaFreeAsync(ta.sync, st);
-  } else {
-    alz_biquad_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK><<<dim3((unsigned)nch, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ca);
-  }
-  ALZ_CUDA(cudaGetLastError());
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return ALZ_OK;
-}
-
-template <int K, int NB, int MONIC, int NB0, int ZMASK>
-static int launch_biquad_t(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
-  const int stride = ALZ_COEF_STRIDE(K, NB0);
-  const bool small = p->C * stride <= kCoefSmall;
-  const int per_launch = (small ? kCoefSmall : kCoefLarge) / stride;
-  for (int c0 = 0; c0 < p->C; c0 += per_launch) {
-    const int nch = std::min(per_launch, p->C - c0);
-    const int rc = small ? launch_biquad_chunk<K, NB, MONIC, kCoefSmall, NB0, ZMASK>(p, ta, state, sstride, c0, nch, st)
-                         : launch_biquad_chunk<K, NB, MONIC, kCoefLarge, NB0, ZMASK>(p, ta, state, sstride, c0, nch, st);
-    if (rc != ALZ_OK) return rc;
-  }
-  return ALZ_OK;
-}
-
-template <int K, int NB, int NB0, int ZMASK = 0>
-static int launch_biquad_nb(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
-  if (p->monic == 2) return launch_biquad_t<K, NB, 2, NB0, ZMASK>(p, ta, state, sstride, st);
-  if (p->monic == 1) return launch_biquad_t<K, NB, 1, NB0, ZMASK>(p, ta, state, sstride, st);
-  return launch_biquad_t<K, NB, 0, NB0, ZMASK>(p, ta, state, sstride, st);
-}
-template <int K>
-static int launch_biquad_k(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
-  switch (p->NB) {
-    case 1: return launch_biquad_nb<K, 1, 0>(p, ta, state, sstride, st);
-    case 2: return launch_biquad_nb<K, 2, 0>(p, ta, state, sstride, st);
-    default:
-      if constexpr (K == 4) {
-        if ((p->zmask & ALZ_ZMASK_KLAPURI) == ALZ_ZMASK_KLAPURI)
-          return launch_biquad_nb<4, 3, 0, ALZ_ZMASK_KLAPURI>(p, ta, state, sstride, st);
-      }
-      return launch_biquad_nb<K, 3, 0>(p, ta, state, sstride, st);
-  }
-}
-// head-FIR plans: first section with up to 8 numerator taps (K in {1, 4}, NB in {1, 3})
-template <int K>
-static int launch_headfir_k(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
-  if (p->NB <= 1) return launch_biquad_nb<K, 1, 8>(p, ta, state, sstride, st);
-  return launch_biquad_nb<K, 3, 8>(p, ta, state, sstride, st);
-}
-static int launch_biquad(const alz_plan* p, const AlzTileArgs& ta, double* state, long long sstride, cudaStream_t st) {
+static int launch_biquad(const alz_plan* p, const AlzTileArgs& ta, cudaStream_t st) {
   if (p->NB0 == 8) {
-    if (p->K == 1) return launch_headfir_k<1>(p, ta, state, sstride, st);
-    if (p->K == 4) return launch_headfir_k<4>(p, ta, state, sstride, st);
+    if (p->K == 1) return alzi_launch_headfir_k1(p, ta, st);
+    if (p->K == 4) return alzi_launch_headfir_k4(p, ta, st);
     return fail(ALZ_ERR_UNSUPPORTED, "no head-FIR kernel for K=%d", p->K);
   }
   switch (p->K) {
-    case 1: return launch_biquad_k<1>(p, ta, state, sstride, st);
-    case 2: return launch_biquad_k<2>(p, ta, state, sstride, st);
-    case 3: return launch_biquad_k<3>(p, ta, state, sstride, st);
-    case 4: return launch_biquad_k<4>(p, ta, state, sstride, st);
-    case 6: return launch_biquad_k<6>(p, ta, state, sstride, st);
-    case 8: return launch_biquad_k<8>(p, ta, state, sstride, st);
+    case 1: return alzi_launch_biquad_k1(p, ta, st);
+    case 2: return alzi_launch_biquad_k2(p, ta, st);
+    case 3: return alzi_launch_biquad_k3(p, ta, st);
+    case 4: return alzi_launch_biquad_k4(p, ta, st);
+    case 6: return alzi_launch_biquad_k6(p, ta, st);
+    case 8: return alzi_launch_biquad_k8(p, ta, st);
   }
   return fail(ALZ_ERR_UNSUPPORTED, "no biquad kernel for K=%d", p->K);
 }
 
-static int launch_generic(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, cudaStream_t st,
-                          const double* tv = nullptr, long long tv_stride = 0) {
-  AlzGenericArgs ga{p->d_sec, p->d_tap_delay, p->d_coef, state, sstride, p->K, p->C, 0, tv, tv_stride};
-  ta.c_base = 0;
+static double probe_biquad(const alz_plan* p, const double* r64, const double* r32) {
+  if (p->NB0 == 8) return p->K == 1 ? alzi_probe_headfir_k1(p, r64, r32) : alzi_probe_headfir_k4(p, r64, r32);
+  switch (p->K) {
+    case 1: return alzi_probe_biquad_k1(p, r64, r32);
+    case 2: return alzi_probe_biquad_k2(p, r64, r32);
+    case 3: return alzi_probe_biquad_k3(p, r64, r32);
+    case 4: return alzi_probe_biquad_k4(p, r64, r32);
+    case 6: return alzi_probe_biquad_k6(p, r64, r32);
+    default: return alzi_probe_biquad_k8(p, r64, r32);
+  }
+}
+
+static int launch_generic(const alz_plan* p, AlzTileArgs ta, cudaStream_t st, const double* tv = nullptr,
+                          long long tv_stride = 0) {
+  AlzGenericArgs ga{p->d_sec, p->d_tap_delay, p->d_coef, p->K, p->C, 0, tv, tv_stride};
   const long long groups = (ta.S + 31) / 32;
   CUtensorMap tmx, tmy;
-  if (make_tensor_maps(ta, &tmx, &tmy))
+  if (alzi_make_tensor_maps(ta, &tmx, &tmy))
     alz_generic_tma_kernel<<<dim3((unsigned)p->C, (unsigned)groups), 32, ALZ_TMA_SMEM, st>>>(ta, ga, tmx, tmy);
   else
     alz_generic_kernel<<<dim3((unsigned)p->C, (unsigned)groups), 32, ALZ_WARP_SMEM, st>>>(ta, ga);
@@ -356,8 +191,9 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
   if (!out) return fail(ALZ_ERR_INVALID, "out is null");
   *out = nullptr;
   if (!coef || !desc || C <= 0 || KM < 0) return fail(ALZ_ERR_INVALID, "bad plan arguments");
-  int dev = 0;
-  ALZ_CUDA(cudaGetDevice(&dev));
+  const bool design_only = (flags & ALZ_PLAN_DESIGN_ONLY) != 0;   // tables and tier decision only: no device is touched
+  int dev = -1;
+  if (!design_only) ALZ_CUDA(cudaGetDevice(&dev));
 
   // ---- normalise every section: divide by a0, trim trailing zeros ------------------
   struct Sec { std::vector<double> b, a; };   // a[0] == 1 after normalisation (kept for indexing)
@@ -399,7 +235,7 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
   if (!p) return fail(ALZ_ERR_NOMEM, "out of host memory");
   p->C = C;
   p->device = dev;
-  if (cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || p->sm_count <= 0) {
+  if (design_only || cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || p->sm_count <= 0) {
     cudaGetLastError();
     p->sm_count = 148;
   }
@@ -463,11 +299,11 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
       p->zmask = zm;
       if (K == 4 && p->NB == 3 && (zm & ALZ_ZMASK_KLAPURI) == ALZ_ZMASK_KLAPURI) p->fp64_ops -= 6;   // the kernel that skips them
     }
-    const int stride = ALZ_COEF_STRIDE(K, p->NB0);
-    p->h_tab.assign((size_t)C * stride, 0.0);
+    const int stride = ALZ_COEF_STRIDE(K, p->NB0), nval = ALZ_COEF_NVAL(K, p->NB0);
+    std::vector<double> tab((size_t)C * stride, 0.0);     // channel order, float64 records
     p->sc.assign((size_t)C * (K + 1), 1.0);
     for (int c = 0; c < C; ++c) {
-      double* rec = p->h_tab.data() + (size_t)c * stride;
+      double* rec = tab.data() + (size_t)c * stride;
       double g = 1.0, sc = 1.0;
       if (p->monic == 2) {   // working units start at the (float32-rounded) gain applied to the input
         double gg = 1.0;
@@ -502,6 +338,66 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
       }
       rec[5 * K] = monic ? g : 1.0;
     }
+    // ---- precision tier per channel: MEASURED, not guessed -----------------------------------
+    // A channel runs its recurrence in float32 (FP32 pipe, no conversions) only if the float32 core,
+    // executed here on the host with the kernel's own arithmetic, stays within tier_tol of the float64
+    // core on the probe signals; tier_tol defaults to a quarter of the 1e-5 parity bar.  Poles close
+    // to z = 1 (low ERB channels) fail by orders of magnitude and stay in float64.
+    p->tier.assign(C, 0);
+    p->tier_err.assign(C, -1.0);
+    p->tier_tol = env_double("ALZ_TIER_TOL", 2.5e-6);
+    p->probe_len = std::max(64, env_int("ALZ_TIER_PROBE", 8192));
+    const bool tiering = !(flags & ALZ_PLAN_EXACT) && !env_int("ALZ_NO_FP32_TIER", 0) && p->tier_tol > 0.0;
+    std::vector<double> tab32((size_t)C * stride, 0.0);   // the same records as packed floats
+    for (int c = 0; c < C; ++c) {
+      const double* rec = tab.data() + (size_t)c * stride;
+      float* r32 = reinterpret_cast<float*>(tab32.data() + (size_t)c * stride);
+      bool representable = true;
+      for (int i = 0; i < nval; ++i) {
+        r32[i] = (float)rec[i];
+        if (rec[i] != 0.0 && !(std::fabs(rec[i]) > 1e-30 && std::fabs(rec[i]) < 1e30)) representable = false;
+      }
+      if (tiering && representable) {
+        p->tier_err[c] = probe_biquad(p, rec, tab32.data() + (size_t)c * stride);
+        if (p->tier_err[c] <= p->tier_tol) { p->tier[c] = 1; ++p->n_fp32; }
+      }
+    }
+    // ---- positions: interleave the tiers along blockIdx.x so both kinds of warp share every SM ----
+    {
+      std::vector<int> lst[2];
+      for (int c = 0; c < C; ++c) lst[p->tier[c]].push_back(c);
+      size_t i0 = 0, i1 = 0;
+      p->pos_channel.clear();
+      while (i0 < lst[0].size() || i1 < lst[1].size()) {   // Bresenham merge: the list that is less consumed goes next
+        const bool take0 = i1 >= lst[1].size() || (i0 < lst[0].size() && i0 * lst[1].size() <= i1 * lst[0].size());
+        p->pos_channel.push_back(take0 ? lst[0][i0++] : lst[1][i1++]);
+      }
+    }
+    p->h_tab.assign((size_t)C * stride, 0.0);
+    for (int pos = 0; pos < C; ++pos) {
+      const int c = p->pos_channel[pos];
+      const std::vector<double>& src = p->tier[c] ? tab32 : tab;
+      double* rec = p->h_tab.data() + (size_t)pos * stride;
+      memcpy(rec, src.data() + (size_t)c * stride, (size_t)nval * sizeof(double));
+      rec[ALZ_COEF_META(K, p->NB0)] = (double)(c + 65536 * p->tier[c]);
+    }
+    p->fp64_ops_exact = p->fp64_ops;
+    // ---- kernel-parameter blocks, built once (launches pass them by address) ---------------------
+    p->coef_small = C * stride <= kCoefSmall;
+    const int ncoef = p->coef_small ? kCoefSmall : kCoefLarge;
+    const int per_launch = ncoef / stride;
+    if (per_launch < 1) { alz_plan_destroy(p); return fail(ALZ_ERR_UNSUPPORTED, "coefficient record too large"); }
+    for (int p0 = 0; p0 < C; p0 += per_launch) {
+      const int npos = std::min(per_launch, C - p0);
+      char* blk = (char*)calloc(1, 2 * sizeof(int) + (size_t)ncoef * sizeof(double));
+      if (!blk) { alz_plan_destroy(p); return fail(ALZ_ERR_NOMEM, "out of host memory"); }
+      reinterpret_cast<int*>(blk)[0] = stride;
+      reinterpret_cast<int*>(blk)[1] = npos;
+      memcpy(blk + 2 * sizeof(int), p->h_tab.data() + (size_t)p0 * stride, (size_t)npos * stride * sizeof(double));
+      p->chunks.push_back({blk, npos});
+    }
+    p->tile_group = env_int("ALZ_TILE_GROUP", 2);
+    if (p->tile_group != 1 && p->tile_group != 2 && p->tile_group != 4) p->tile_group = 2;
   } else {
     // ---- generic: union tap structure per section --------------------------------
     const int K = Kmax;
@@ -565,7 +461,8 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
     p->h_tap_delay = tap_delay;
     std::vector<double> tab(ntaps * C);
     for (size_t t = 0; t < ntaps; ++t) memcpy(&tab[t * C], tap_coef[t].data(), C * sizeof(double));
-    cudaError_t e = cudaMalloc(&p->d_coef, tab.size() * sizeof(double));
+    cudaError_t e = design_only ? cudaSuccess : cudaMalloc(&p->d_coef, tab.size() * sizeof(double));
+    if (design_only) { *out = p; return ALZ_OK; }
     if (e == cudaSuccess) e = cudaMemcpy(p->d_coef, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_sec, K * sizeof(AlzGenSection));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_sec, p->h_sec.data(), K * sizeof(AlzGenSection), cudaMemcpyHostToDevice);
@@ -579,16 +476,22 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
 
 void alz_plan_destroy(alz_plan* p) {
   if (!p) return;
+  if (p->device < 0) {   // design-only: host tables only
+    for (auto& ch : p->chunks) free(ch.block);
+    delete p;
+    return;
+  }
   int cur = 0;
   cudaGetDevice(&cur);
   cudaSetDevice(p->device);
   if (p->pipe.ready) {
-    for (int i = 0; i < HostPipe::NBUF; ++i) {
+    for (int i = 0; i < AlzHostPipe::NBUF; ++i) {
       if (p->pipe.stream[i]) { cudaStreamSynchronize(p->pipe.stream[i]); cudaStreamDestroy(p->pipe.stream[i]); }
       cudaFree(p->pipe.dx[i]);
       cudaFree(p->pipe.dy[i]);
     }
   }
+  for (auto& ch : p->chunks) free(ch.block);
   cudaFree(p->d_coef);
   cudaFree(p->d_sec);
   cudaFree(p->d_tap_delay);
@@ -611,7 +514,19 @@ int32_t alz_plan_info_get(const alz_plan* p, alz_plan_info* out) {
   out->state_doubles = p->state_doubles;
   out->fp64_ops = p->fp64_ops;
   out->device = p->device;
+  out->n_fp32_channels = p->n_fp32;
+  out->tier_tol_e9 = (int32_t)std::min(2.0e9, p->tier_tol * 1e9 + 0.5);
   return ALZ_OK;
+}
+
+int32_t alz_plan_tiers(const alz_plan* p, int32_t* tier, double* probe_err, int32_t cap) {
+  if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  for (int c = 0; c < p->C && c < cap; ++c) {
+    const bool have = c < (int)p->tier.size();
+    if (tier) tier[c] = have ? p->tier[c] : 0;
+    if (probe_err) probe_err[c] = have ? p->tier_err[c] : -1.0;
+  }
+  return p->C;
 }
 
 int64_t alz_plan_state_doubles(const alz_plan* p, int64_t S) {
@@ -637,6 +552,7 @@ static __global__ void alz_state_fill_kernel(double* state, const double* proto,
 int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double* xinit, const double* yinit,
                        void* cuda_stream) {
   if (!p || S < 0) return fail(ALZ_ERR_INVALID, "bad argument");
+  if (p->device < 0) return fail(ALZ_ERR_CUDA, "design-only plan: no device");
   if (S == 0) return ALZ_OK;
   if (!state) return fail(ALZ_ERR_INVALID, "state is null");
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -692,8 +608,9 @@ int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double
 
 static int apply_launch(const alz_plan* p, AlzTileArgs ta, double* state, long long sstride, cudaStream_t st,
                         const double* tv, long long tv_stride) {
-  return p->kind == ALZ_KIND_BIQUAD ? launch_biquad(p, ta, state, sstride, st)
-                                    : launch_generic(p, ta, state, sstride, st, tv, tv_stride);
+  ta.state = state;
+  ta.sstride = sstride;
+  return p->kind == ALZ_KIND_BIQUAD ? launch_biquad(p, ta, st) : launch_generic(p, ta, st, tv, tv_stride);
 }
 
 // ---- time-parallel evaluation of FEW long streams ------------------------------------------
@@ -817,7 +734,7 @@ static int apply_impl(const alz_plan* p, const float* x, float* y, double* state
                       long long tv_stride = 0) {
   if (!tv && chunked_applies(p, S, T)) return apply_chunked(p, x, y, state, sstride, S, T, xs, ys, st);
   AlzTileArgs ta{};
-  ta.T = T; ta.xs = xs; ta.ys = ys; ta.ysS = (long long)p->C * ys; ta.C = p->C; ta.c_base = 0;
+  ta.T = T; ta.xs = xs; ta.ys = ys; ta.ysS = (long long)p->C * ys; ta.C = p->C;
   ta.Stot = sstride / p->C;
   ta.vec_in = (((uintptr_t)x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
   ta.vec_out = (((uintptr_t)y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
@@ -836,6 +753,7 @@ static int apply_impl(const alz_plan* p, const float* x, float* y, double* state
 int32_t alz_apply_f32(const alz_plan* p, const float* x, float* y, double* state, int64_t S, int64_t T,
                       int64_t xs, int64_t ys, void* cuda_stream) {
   if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (p->device < 0) return fail(ALZ_ERR_CUDA, "design-only plan: no device");
   if (S < 0 || T < 0) return fail(ALZ_ERR_INVALID, "negative size");
   if (S == 0 || T == 0) return ALZ_OK;
   if (!x || !y || !state) return fail(ALZ_ERR_INVALID, "null buffer");
@@ -880,13 +798,14 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
                            int64_t xs, int64_t ys) {
   alz_plan* p = const_cast<alz_plan*>(cp);
   if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (p->device < 0) return fail(ALZ_ERR_CUDA, "design-only plan: no device");
   if (S < 0 || T < 0) return fail(ALZ_ERR_INVALID, "negative size");
   if (S == 0 || T == 0) return ALZ_OK;
   if (!xh || !yh) return fail(ALZ_ERR_INVALID, "null buffer");
   if (xs < T || ys < T) return fail(ALZ_ERR_INVALID, "row stride shorter than n_samples");
   std::lock_guard<std::mutex> lock(p->host_mu);
   ALZ_CUDA(cudaSetDevice(p->device));
-  HostPipe& hp = p->pipe;
+  AlzHostPipe& hp = p->pipe;
   const long long C = p->C;
   const long long kChunkBytes = 128LL << 20;   // <= 128 MiB of output per staged chunk
   // a chunk is (streams [s0, s0+Sc)) x (samples [t0, t0+Tc)): whole streams when they are short,
@@ -902,17 +821,17 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
   if (Sc > S) Sc = S;
   const size_t need_x = (size_t)Sc * Tp * 4, need_y = (size_t)Sc * C * Tp * 4;
   if (!hp.ready) {
-    for (int i = 0; i < HostPipe::NBUF; ++i) ALZ_CUDA(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < AlzHostPipe::NBUF; ++i) ALZ_CUDA(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
     hp.ready = true;
   }
   if (hp.dx_bytes < need_x || hp.dy_bytes < need_y) {
-    for (int i = 0; i < HostPipe::NBUF; ++i) {
+    for (int i = 0; i < AlzHostPipe::NBUF; ++i) {
       ALZ_CUDA(cudaStreamSynchronize(hp.stream[i]));
       cudaFree(hp.dx[i]); hp.dx[i] = nullptr;
       cudaFree(hp.dy[i]); hp.dy[i] = nullptr;
     }
     hp.dx_bytes = hp.dy_bytes = 0;
-    for (int i = 0; i < HostPipe::NBUF; ++i) {
+    for (int i = 0; i < AlzHostPipe::NBUF; ++i) {
       ALZ_CUDA(cudaMalloc(&hp.dx[i], need_x));
       ALZ_CUDA(cudaMalloc(&hp.dy[i], need_y));
     }
@@ -934,7 +853,7 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
     cudaEvent_t prev = nullptr;   // time segments of the same streams must run in order (state dependency)
     for (long long t0 = 0; t0 < T && rc == ALZ_OK; t0 += Tc, ++i) {
       const long long nt = std::min<long long>(Tc, T - t0);
-      const int b = i % HostPipe::NBUF;
+      const int b = i % AlzHostPipe::NBUF;
       cudaStream_t st = hp.stream[b];
       if (prev) { cudaStreamWaitEvent(st, prev, 0); cudaEventDestroy(prev); prev = nullptr; }
       cudaError_t e = cudaMemcpy2DAsync(hp.dx[b], Tp * 4, xh + s0 * xs + t0, xs * 4, nt * 4, n, cudaMemcpyHostToDevice, st);
@@ -950,7 +869,7 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
     }
     if (prev) cudaEventDestroy(prev);
   }
-  for (int k = 0; k < HostPipe::NBUF; ++k) {
+  for (int k = 0; k < AlzHostPipe::NBUF; ++k) {
     cudaError_t e = cudaStreamSynchronize(hp.stream[k]);
     if (e != cudaSuccess && rc == ALZ_OK) rc = fail(ALZ_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
   }
@@ -1020,6 +939,7 @@ static __global__ void alz_freq_response_kernel(const double* __restrict__ coef,
 
 int32_t alz_freq_response_f64(alz_plan* p, const double* w, double* out, int64_t n, void* cuda_stream) {
   if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (p->device < 0) return fail(ALZ_ERR_CUDA, "design-only plan: no device");
   if (n < 0) return fail(ALZ_ERR_INVALID, "negative size");
   if (n == 0) return ALZ_OK;
   if (!w || !out) return fail(ALZ_ERR_INVALID, "null buffer");

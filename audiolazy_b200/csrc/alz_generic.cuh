@@ -28,8 +28,6 @@ struct AlzGenericArgs {
   const AlzGenSection* sec;   // [K]
   const int* tap_delay;       // [ntaps]
   const double* coef;         // [ntaps][C]
-  double* state;              // slot 0 = absolute sample count
-  long long sstride;
   int K;
   int C;
   int c_base;
@@ -37,6 +35,7 @@ struct AlzGenericArgs {
   // sample j of THIS launch uses tv[i * tv_stride + j] instead of coef[i][c] (C must be 1)
   const double* tv;
   long long tv_stride;
+  __device__ __forceinline__ int channel(int pos) const { return c_base + pos; }
 };
 
 struct AlzGenericCore {
@@ -51,14 +50,14 @@ struct AlzGenericCore {
   long long tv_stride;
   bool live;   // lanes beyond the last stream must not touch the (clamped) state rows
 
-  __device__ __forceinline__ void load(const AlzGenericArgs& ca, long long r, int c_local, bool valid) {
+  __device__ __forceinline__ void load(const AlzTileArgs& a, const AlzGenericArgs& ca, long long r, int c_local, bool valid) {
     sec = ca.sec;
     tap_delay = ca.tap_delay;
     K = ca.K;
     C = ca.C;
-    R = ca.sstride;
+    R = a.sstride;               // state slot 0 = absolute sample count
     cf = ca.coef + (ca.c_base + c_local);
-    st = ca.state + r;
+    st = a.state + r;
     cnt0 = (long long)st[0];
     tv = ca.tv;
     tv_stride = ca.tv_stride;
@@ -100,5 +99,5 @@ struct AlzGenericCore {
     }
   }
 
-  __device__ __forceinline__ void store(const AlzGenericArgs&, long long, long long T) { st[0] = (double)(cnt0 + T); }
+  __device__ __forceinline__ void store(const AlzTileArgs&, long long, long long T) { st[0] = (double)(cnt0 + T); }
 };

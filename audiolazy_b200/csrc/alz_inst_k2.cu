@@ -1,0 +1,4 @@
+// Biquad kernels for cascades of K = 2 sections (see alz_launch.cuh).
+#include "alz_launch.cuh"
+int alzi_launch_biquad_k2(const alz_plan* p, const AlzTileArgs& ta, cudaStream_t st) { return launch_biquad_k<2>(p, ta, st); }
+double alzi_probe_biquad_k2(const alz_plan* p, const double* r64, const double* r32) { return probe_biquad_k<2>(p, r64, r32); }

@@ -1,0 +1,4 @@
+// Biquad kernels for cascades of K = 6 sections (see alz_launch.cuh).
+#include "alz_launch.cuh"
+int alzi_launch_biquad_k6(const alz_plan* p, const AlzTileArgs& ta, cudaStream_t st) { return launch_biquad_k<6>(p, ta, st); }
+double alzi_probe_biquad_k6(const alz_plan* p, const double* r64, const double* r32) { return probe_biquad_k<6>(p, r64, r32); }

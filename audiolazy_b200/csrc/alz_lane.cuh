@@ -43,6 +43,8 @@ struct AlzTileArgs {
   long long S, T, xs, ys;
   long long ysS;    // y stride between consecutive STREAMS (C*ys for the dense [S][C][T] layout)
   long long Stot;   // streams the state buffer was sized for: recurrence index r = c * Stot + s
+  double* state;    // state[slot * sstride + r] (float64 working-unit values, in/out)
+  long long sstride;   // slot stride of the state buffer (recurrences it was sized for)
   // Time segmentation (TMA engine only; nseg <= 1 = off).  The grid is (channels, groups*nseg);
   // a CTA draws a ticket from its channel's counter, tickets map to (segment, group) segment-major,
   // and segment k of a (channel, group) waits for the flag its segment k-1 raises after storing
@@ -51,13 +53,12 @@ struct AlzTileArgs {
   int groups;            // stream groups of this launch = ceil(S / 32)
   long long seg_len;     // samples per segment (multiple of 32)
   unsigned* sync;        // [channels of this launch] tickets, then [channels][groups] flags; zeroed per launch
-  // TMA engine: 1 = tiles in pairs (both loads issued together, both stores back to back: each
-  // output row receives 256 contiguous bytes at once, +13 % HBM write efficiency, but no prefetch
-  // under the compute of the same warp -- for launches that fill the machine); 0 = one tile at a
-  // time with the next one prefetched (latency-bound launches).
+  // TMA engine: 2 / 4 = tiles in groups of that many (all loads issued together, all stores back to
+  // back: each output row receives 256 / 512 contiguous bytes at once, better HBM write efficiency,
+  // but no prefetch under the compute of the same warp -- for launches that fill the machine);
+  // 0 / 1 = one tile at a time with the next one prefetched (latency-bound launches).
   int paired;
   int C;            // channels of the whole bank (output row index = s*C + c)
-  int c_base;       // first channel handled by this launch (blockIdx.x + c_base = c)
   int vec_in;       // 1: x rows are 16-byte aligned (16 B cp.async), 0: 4 B cp.async
   int vec_out;      // 1: y rows are 16-byte aligned (st.v4), 0: scalar stores
 };
@@ -113,24 +114,25 @@ __device__ __forceinline__ void alz_issue_tile(const AlzTileArgs& a, float* buf,
 
 // Core concept:
 //   struct Core {
-//     __device__ void load(const CoreArgs&, long long r /* = c*Stot + s */, int c_local, bool valid);
+//     __device__ void load(const AlzTileArgs&, const CoreArgs&, long long r /* = c*Stot + s */, int c_local, bool valid);
 //     __device__ void tile(float* row, int swz, int nvalid, long long n_done);
 //         // row[0..nvalid) holds float32 inputs; overwrite them with float32 outputs.
 //         // n_done = samples already processed in this launch (warp-uniform).
-//     __device__ void store(const CoreArgs&, long long r, long long T);
+//     __device__ void store(const AlzTileArgs&, long long r, long long T);
 //   };
+//   CoreArgs::channel(pos): bank channel handled by grid position pos = blockIdx.x.
 template <class Core, class CoreArgs>
 __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArgs& ca, float* smem) {
   const int lane = threadIdx.x;
   const int c_local = blockIdx.x;              // CTA-uniform: coefficients go to uniform registers
-  const int c = a.c_base + c_local;
+  const int c = ca.channel(c_local);           // the plan orders positions so that precision tiers interleave
   const long long s0 = (long long)blockIdx.y * 32;
   const long long s = s0 + lane;
   const bool valid = s < a.S;
   const long long r = (long long)c * a.Stot + (valid ? s : a.S - 1);   // stream-fastest: coalesced state access
 
   Core core;
-  core.load(ca, r, c_local, valid);
+  core.load(a, ca, r, c_local, valid);
 
   const long long ntiles = (a.T + ALZ_TT - 1) / ALZ_TT;
   const long long nfull = a.T / ALZ_TT;
@@ -188,5 +190,5 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
     alz_cp_commit();
   }
   alz_cp_wait<0>();
-  if (valid) core.store(ca, r, a.T);
+  if (valid) core.store(a, r, a.T);
 }

@@ -17,7 +17,9 @@
 #include "alz_lane.cuh"
 
 #define ALZ_TMA_TILE_BYTES 4096                      // 32 rows x 128 B
-#define ALZ_TMA_SMEM (2 * ALZ_TMA_TILE_BYTES + 16)   // two tiles + two mbarriers
+#define ALZ_TMA_MAX_GROUP 4                          // tiles moved together (AlzTileArgs::paired)
+#define ALZ_TMA_SMEM_FOR(ng) (((ng) < 2 ? 2 : (ng)) * ALZ_TMA_TILE_BYTES + 8 * ALZ_TMA_MAX_GROUP)   // tiles + mbarriers
+#define ALZ_TMA_SMEM ALZ_TMA_SMEM_FOR(2)
 
 __device__ __forceinline__ unsigned alz_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -56,7 +58,7 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
                                                  const CUtensorMap* tmy, unsigned char* smem) {
   const int lane = threadIdx.x;
   const int c_local = blockIdx.x;              // CTA-uniform: coefficients go to uniform registers
-  const int c = a.c_base + c_local;
+  const int c = ca.channel(c_local);           // the plan orders positions so that precision tiers interleave
   int group = blockIdx.y, seg = 0;
   long long tbeg = 0, tlen = a.T;
   unsigned* flag = nullptr;
@@ -83,84 +85,89 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   const bool valid = s < a.S;
   const long long r = (long long)c * a.Stot + (valid ? s : a.S - 1);   // stream-fastest: coalesced state access
 
+  const int NG = a.paired < 2 ? 1 : a.paired;   // tiles per group (1 = one tile at a time with a prefetch)
+  const int nbuf = NG < 2 ? 2 : NG;
   const unsigned tile0 = alz_smem_u32(smem);
-  const unsigned mbar0 = tile0 + 2 * ALZ_TMA_TILE_BYTES;
+  const unsigned mbar0 = tile0 + nbuf * ALZ_TMA_TILE_BYTES;
   if (lane == 0) {
-    alz_mbar_init(mbar0, 1);
-    alz_mbar_init(mbar0 + 8, 1);
+    for (int j = 0; j < nbuf; ++j) alz_mbar_init(mbar0 + 8 * j, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncwarp();
 
   Core core;
-  core.load(ca, r, c_local, valid);
+  core.load(a, ca, r, c_local, valid);
 
   const int ntiles = (int)((tlen + ALZ_TT - 1) / ALZ_TT);
   const int nfull = (int)(tlen / ALZ_TT);
   const int tb = (int)tbeg;
   const int swz = lane & 7;
   float* const myrow = reinterpret_cast<float*>(smem) + lane * 32;
+  const bool tail_by_lanes = (a.T & 3) != 0 && nfull < ntiles;   // see below: the TMA clips at 16-byte granularity
+  int last_buf = 0;
 
-  const bool paired = a.paired != 0;
-  const bool tail_by_lanes = (a.T & 3) != 0 && nfull < ntiles;
-  if (lane == 0 && !paired) {   // tile 0 in flight
+  // NG == 1: one tile at a time, the next one prefetched into the other buffer (latency-bound launches).
+  // NG >= 2: tiles go in groups of NG (a power of two): all loads are issued together once the previous
+  // group's stores have been read out of shared memory, the tiles are filtered as they land, and all
+  // stores are issued back to back, so each output row receives NG * 128 contiguous bytes at (nearly)
+  // the same time (HBM write efficiency grows with the piece length,
+  // profiles/r01_microbench_hbm_write.txt).  The load of the next group is exposed to this warp; the
+  // other resident warps hide it.
+  const int lg = NG >= 4 ? 2 : (NG >= 2 ? 1 : 0);
+  if (lane == 0 && NG == 1) {   // tile 0 in flight
     alz_mbar_expect_tx(mbar0, ALZ_TMA_TILE_BYTES);
     alz_tma_load_2d(tile0, tmx, tb, (int)s0, mbar0);
   }
-
   for (int i = 0; i < ntiles; ++i) {
-    const int b = i & 1;
+    const int j = NG == 1 ? (i & 1) : (i & (NG - 1));   // buffer of tile i
     const int t0 = i * ALZ_TT;
     if (lane == 0) {
-      if (paired) {
-        // Tiles go in pairs: both loads are issued together once the previous pair's stores have
-        // been read out of shared memory, and both stores are issued back to back after the second
-        // tile, so each output row receives 256 contiguous bytes at (nearly) the same time.
-        if (b == 0) {
-          if (i >= 2) alz_bulk_wait_read0();
-          alz_mbar_expect_tx(mbar0, ALZ_TMA_TILE_BYTES);
-          alz_tma_load_2d(tile0, tmx, tb + t0, (int)s0, mbar0);
-          if (i + 1 < ntiles) {
-            alz_mbar_expect_tx(mbar0 + 8, ALZ_TMA_TILE_BYTES);
-            alz_tma_load_2d(tile0 + ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, (int)s0, mbar0 + 8);
-          }
+      if (NG == 1) {
+        if (i + 1 < ntiles) {
+          // The other buffer was the source of the TMA store of tile i-1: wait until the store has
+          // finished READING it (it was issued a whole barrier-wait ago, so this normally does not block).
+          if (i >= 1) alz_bulk_wait_read0();
+          alz_mbar_expect_tx(mbar0 + 8 * (j ^ 1), ALZ_TMA_TILE_BYTES);
+          alz_tma_load_2d(tile0 + (j ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, (int)s0, mbar0 + 8 * (j ^ 1));
         }
-      } else if (i + 1 < ntiles) {
-        // Prefetch tile i+1 into the other buffer.  That buffer was the source of the TMA
-        // store of tile i-1: wait until the store has finished READING it (it was issued a
-        // whole barrier-wait ago, so this normally does not block).
-        if (i >= 1) alz_bulk_wait_read0();
-        alz_mbar_expect_tx(mbar0 + 8 * (b ^ 1), ALZ_TMA_TILE_BYTES);
-        alz_tma_load_2d(tile0 + (b ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, (int)s0, mbar0 + 8 * (b ^ 1));
+      } else if (j == 0) {
+        if (i > 0) alz_bulk_wait_read0();
+        const int n = ntiles - i < NG ? ntiles - i : NG;
+        for (int jj = 0; jj < n; ++jj) {
+          alz_mbar_expect_tx(mbar0 + 8 * jj, ALZ_TMA_TILE_BYTES);
+          alz_tma_load_2d(tile0 + jj * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + jj * ALZ_TT, (int)s0, mbar0 + 8 * jj);
+        }
       }
     }
-    alz_mbar_wait(mbar0 + 8 * b, (i >> 1) & 1);     // tile i has landed (async proxy writes visible after the wait)
+    alz_mbar_wait(mbar0 + 8 * j, (NG == 1 ? (i >> 1) : (i >> lg)) & 1);   // tile i has landed (async proxy writes visible after the wait)
     const int nvalid = i < nfull ? ALZ_TT : (int)(tlen - t0);
-    core.tile(myrow + b * (ALZ_TMA_TILE_BYTES / 4), swz, nvalid, t0);
+    core.tile(myrow + j * (ALZ_TMA_TILE_BYTES / 4), swz, nvalid, t0);
     alz_fence_async_smem();                          // my generic-proxy writes -> visible to the TMA store
     __syncwarp();
-    const bool by_lanes = tail_by_lanes && i + 1 == ntiles;   // ragged last tile: stored after the loop
+    const bool last = i + 1 == ntiles;
     if (lane == 0) {
-      if (!paired) {
-        if (!by_lanes) alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
+      if (NG == 1) {
+        if (!(tail_by_lanes && last)) alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + j * ALZ_TMA_TILE_BYTES);   // ragged last tile: stored after the loop
         alz_bulk_commit();
-      } else if (b == 1 || i + 1 == ntiles) {
-        if (b == 1) alz_tma_store_3d(tmy, tb + t0 - ALZ_TT, c, (int)s0, tile0);
-        if (!by_lanes) alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + b * ALZ_TMA_TILE_BYTES);
+      } else if (j == NG - 1 || last) {
+        for (int jj = 0; jj <= j; ++jj)
+          if (!(tail_by_lanes && last && jj == j))
+            alz_tma_store_3d(tmy, tb + t0 - (j - jj) * ALZ_TT, c, (int)s0, tile0 + jj * ALZ_TMA_TILE_BYTES);
         alz_bulk_commit();
       }
     }
+    last_buf = j;
   }
   if (tail_by_lanes && valid) {
     // The TMA clips a box at 16-byte granularity: when n_samples is not a multiple of 4 the ragged
     // last tile is written by the lanes themselves (plain stores of the valid samples only).
     const int i = ntiles - 1, t0 = i * ALZ_TT, nvalid = (int)(tlen - t0);
-    const float* src = myrow + (i & 1) * (ALZ_TMA_TILE_BYTES / 4);
+    const float* src = myrow + last_buf * (ALZ_TMA_TILE_BYTES / 4);
     float* dst = a.y + s * a.ysS + (long long)c * a.ys + tbeg + t0;
     for (int j = 0; j < nvalid; ++j) dst[j] = src[(((j >> 2) ^ swz) << 2) | (j & 3)];
   }
   if (lane == 0) alz_bulk_wait0();                   // all output tiles are globally written before exit
-  if (valid) core.store(ca, r, tlen);
+  if (valid) core.store(a, r, tlen);
   if (flag != nullptr && seg + 1 < a.nseg) {         // hand the state to the next segment
     __threadfence();
     __syncwarp();

@@ -1,0 +1,105 @@
+// alz_plan.h -- private to the library: the plan object and the helpers shared by the
+// translation units (alz_capi.cu = the C ABI; alz_inst_*.cu = the biquad kernel instantiations,
+// split by cascade length so that they compile in parallel).  Nothing here is exported.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "alz_generic.cuh"
+#include "alz_lane.cuh"
+
+// status codes of include/alz_b200.h (kept in sync by a static_assert in alz_capi.cu)
+#define ALZI_OK 0
+#define ALZI_ERR_CUDA (-4)
+#define ALZI_ERR_UNSUPPORTED (-6)
+
+int alzi_fail(int code, const char* fmt, ...);
+int alzi_env_int(const char* name, int dflt);
+void alzi_keep_async_pool();
+extern std::atomic<long long> alzi_launches;
+
+#define ALZ_CUDA(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return alzi_fail(ALZI_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct AlzHostPipe {   // lazily created resources of alz_apply_f32_host
+  static const int NBUF = 4;
+  cudaStream_t stream[NBUF] = {};
+  cudaEvent_t done[NBUF] = {};
+  float* dx[NBUF] = {};
+  float* dy[NBUF] = {};
+  size_t dx_bytes = 0, dy_bytes = 0;
+  bool ready = false;
+};
+
+struct alz_plan {
+  int kind = 0, C = 0, K = 0, NB = 0, NB0 = 0, monic = 0, device = 0, sm_count = 148;
+  int zmask = 0;               // biquad: numerator taps that are zero in every channel (AlzBiquadCore ZMASK)
+  int xd = 0, yd = 0;          // history depths exposed to alz_state_init
+  int state_doubles = 0;       // per recurrence
+  int fp64_ops = 0;            // FP64 instructions per channel-sample of a float64-tier channel
+  int fp64_ops_exact = 0;
+  int n_fp32 = 0;              // biquad: channels on the float32 tier
+  double tier_tol = 0.0;       // measured-error threshold the tier decision used
+  int probe_len = 8192;        // samples per probe signal of the tier decision
+  int tile_group = 2;          // TMA engine: tiles moved together by launches that fill the machine (1, 2, 4)
+  bool coef_small = false;     // kernel-parameter block size (kCoefSmall / kCoefLarge doubles)
+  struct Chunk { void* block; int npos; };
+  std::vector<Chunk> chunks;   // biquad: pre-built AlzBiquadArgs<NCOEF> blocks, <= NCOEF / stride positions each
+  // device tables
+  double* d_coef = nullptr;
+  AlzGenSection* d_sec = nullptr;
+  int* d_tap_delay = nullptr;
+  // host copies used by alz_state_init
+  std::vector<double> h_tab;              // biquad: [position][ALZ_COEF_STRIDE] coefficient records (kernel parameters)
+  std::vector<int> pos_channel;           // biquad: position -> channel
+  std::vector<int> tier;                  // biquad: per CHANNEL precision tier (0 float64, 1 float32)
+  std::vector<double> tier_err;           // biquad: per channel measured float32 error (probe), < 0 = not probed
+  std::vector<double> sc;                 // biquad: [C][K+1] working-unit scales
+  std::vector<AlzGenSection> h_sec;       // generic
+  std::vector<int> h_xlen, h_ylen;        // generic: true max delays per section
+  std::vector<int> h_tap_delay, h_tap_is_den;   // generic: tap order of the coefficient table
+  // normalised sections as given (a0 == 1), for alz_freq_response_f64
+  std::vector<double> fr_coef;            // b then a of every (channel, section), concatenated
+  std::vector<int> fr_desc;               // [C][K][3] = nb, na, offset (nb == 0: absent)
+  double* d_fr_coef = nullptr;
+  int fr_K = 0;
+  int* d_fr_desc = nullptr;
+  std::mutex host_mu;
+  AlzHostPipe pipe;
+};
+
+// Biquad launches, one translation unit per cascade length (alz_inst_*.cu).
+int alzi_launch_biquad_k1(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_biquad_k2(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_biquad_k3(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_biquad_k4(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_biquad_k6(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_biquad_k8(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_headfir_k1(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_headfir_k4(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+
+// Plan-time tier probe (host): runs channel records through the SAME core arithmetic in float64
+// and float32 on probe signals, returns the float32 tier's error relative to the row peak.
+// rec64 / rec32: one record each (ALZ_COEF_STRIDE doubles).
+double alzi_probe_biquad_k1(const alz_plan*, const double* rec64, const double* rec32);
+double alzi_probe_biquad_k2(const alz_plan*, const double* rec64, const double* rec32);
+double alzi_probe_biquad_k3(const alz_plan*, const double* rec64, const double* rec32);
+double alzi_probe_biquad_k4(const alz_plan*, const double* rec64, const double* rec32);
+double alzi_probe_biquad_k6(const alz_plan*, const double* rec64, const double* rec32);
+double alzi_probe_biquad_k8(const alz_plan*, const double* rec64, const double* rec32);
+double alzi_probe_headfir_k1(const alz_plan*, const double* rec64, const double* rec32);
+double alzi_probe_headfir_k4(const alz_plan*, const double* rec64, const double* rec32);
+
+// tensor maps of x[S][T] / y[S][C][T] (alz_capi.cu)
+#include <cuda.h>
+bool alzi_make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap* tmy);

@@ -74,7 +74,9 @@ typedef struct alz_plan_info {
   int32_t state_doubles;     /* doubles of state per (stream, channel)                */
   int32_t fp64_ops;          /* FP64 instructions per channel-sample in the hot loop  */
   int32_t device;            /* CUDA device ordinal the plan lives on                 */
-  int32_t reserved[7];
+  int32_t n_fp32_channels;   /* channels whose recurrence runs on the float32 tier (see alz_plan_tiers) */
+  int32_t tier_tol_e9;       /* the tier decision's error threshold, in units of 1e-9 */
+  int32_t reserved[5];
 } alz_plan_info;
 
 /* Thread-local description of the last error returned on this thread. */
@@ -111,12 +113,32 @@ int32_t alz_plan_create(const double* coef, const int32_t* section_desc,
 /* Same with flags.  ALZ_PLAN_FORCE_GENERIC keeps every listed tap (also zero-valued ones are
  * kept if non-zero in any channel) on the generic kernel: required for time-varying plans. */
 #define ALZ_PLAN_FORCE_GENERIC 1
+/* ALZ_PLAN_EXACT: every channel's recurrence in float64 (no float32 precision tier, below). */
+#define ALZ_PLAN_EXACT 2
+/* ALZ_PLAN_DESIGN_ONLY: build the plan's tables and tier decision without touching any device
+ * (works on a host without a GPU); only alz_plan_info_get / alz_plan_tiers / alz_plan_history /
+ * alz_plan_state_doubles / alz_plan_destroy accept such a plan, every compute entry fails. */
+#define ALZ_PLAN_DESIGN_ONLY 4
 int32_t alz_plan_create_ex(const double* coef, const int32_t* section_desc, int32_t n_channels,
                            int32_t max_sections, int32_t flags, alz_plan** out);
 
 void alz_plan_destroy(alz_plan* plan);
 
 int32_t alz_plan_info_get(const alz_plan* plan, alz_plan_info* out);
+
+/*
+ * Precision tiers (biquad plans).  The reference evaluates everything in float64
+ * (lazy_filters.py:197-257 on Python floats); the parity bar of this path is 1e-5 relative to
+ * each output row's peak for float32 I/O.  At plan creation every channel is run, on the host,
+ * through the kernel's own arithmetic in float64 AND in float32 on probe signals (white noise,
+ * step, Nyquist); a channel whose float32 result stays within the threshold (default 2.5e-6 =
+ * a quarter of the bar; ALZ_TIER_TOL) is evaluated in float32 on the device (tier 1: FP32 pipe,
+ * no conversions), all others in float64 (tier 0).  Poles near z = 1 -- low ERB channels -- fail
+ * the probe by orders of magnitude and stay on tier 0.  ALZ_PLAN_EXACT or ALZ_NO_FP32_TIER=1
+ * keep every channel on tier 0.  Fills tier[c] / probe_err[c] (measured float32 error, < 0 when
+ * not probed) for c < min(cap, n_channels); returns n_channels.  Either array may be NULL.
+ */
+int32_t alz_plan_tiers(const alz_plan* plan, int32_t* tier, double* probe_err, int32_t cap);
 
 /* Doubles of device state needed for `n_streams` input streams (>= 0), or <0 on error. */
 int64_t alz_plan_state_doubles(const alz_plan* plan, int64_t n_streams);
