@@ -29,7 +29,8 @@ PLAN_DESIGN_ONLY = 4
 #: every symbol include/alz_b200.h declares (tests check the library exports them all)
 SYMBOLS = (
   "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_create_ex",
-  "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32", "alz_plan_tiers",
+  "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32", "alz_plan_tiers", "alz_apply_f32_ex", "alz_host_alloc",
+  "alz_host_free",
   "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
   "alz_apply_f32_host", "alz_sum_channels_f32", "alz_freq_response_f64", "alz_launch_count",
 )
@@ -91,6 +92,12 @@ def lib():
   L.alz_plan_history.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]
   L.alz_apply_f32.restype = i32
   L.alz_apply_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
+  L.alz_apply_f32_ex.restype = i32
+  L.alz_apply_f32_ex.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp]
+  L.alz_host_alloc.restype = i32
+  L.alz_host_alloc.argtypes = [ctypes.POINTER(vp), i64, i32, ctypes.POINTER(i32)]
+  L.alz_host_free.restype = i32
+  L.alz_host_free.argtypes = [vp]
   L.alz_apply_f32_host.restype = i32
   L.alz_apply_f32_host.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64]
   L.alz_sum_channels_f32.restype = i32
@@ -187,6 +194,12 @@ class Plan(object):
     _check(lib().alz_plan_tiers(self._h, tier.ctypes.data, err.ctypes.data, self.n_channels))
     return tier, err
 
+  def apply_ex(self, x_ptr, y_ptr, state_ptr, n_streams, n_samples, x_stride, y_stride, y_stream_stride, stream=0):
+    """:meth:`apply` with an explicit distance between the output rows of consecutive streams (channel slices
+    written into a wider ``y[S][C_total][T]``, possibly on a peer GPU)."""
+    _check(lib().alz_apply_f32_ex(self._h, x_ptr, y_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),
+                                  int(y_stride), int(y_stream_stride), stream))
+
   def taps(self):
     """``[(delay, is_den), ...]`` in coefficient-table order (generic plans only)."""
     n = _check(lib().alz_plan_taps(self._h, None, None, 0))
@@ -217,6 +230,26 @@ class Plan(object):
     x_stride = x.strides[0] // 4 if S > 1 else max(T, 1)   # a length-1 axis may carry any stride
     _check(lib().alz_apply_f32_host(self._h, x.ctypes.data, y.ctypes.data, state_ptr, S, T, x_stride, T))
     return y
+
+
+class HostBuffer(object):
+  """Pinned float32 host array on the NUMA node of a CUDA device (``alz_host_alloc``): ``.array`` is a numpy view.
+  Call :meth:`free` when done (the memory is not garbage collected while views may exist)."""
+
+  def __init__(self, shape, device=-1):
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    n = int(np.prod(shape)) if shape else 1
+    ptr, node = ctypes.c_void_p(), ctypes.c_int32(-1)
+    _check(lib().alz_host_alloc(ctypes.byref(ptr), max(4, n * 4), int(device), ctypes.byref(node)))
+    self._ptr = ptr
+    self.numa_node = node.value
+    self.array = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_float)), shape=(max(n, 1),))[:n].reshape(shape)
+
+  def free(self):
+    ptr, self._ptr = self._ptr, None
+    if ptr:
+      self.array = None
+      _check(lib().alz_host_free(ptr))
 
 
 def sum_channels(y_ptr, out_ptr, n_streams, n_channels, n_samples, y_stride, out_stride, stream=0):

@@ -41,12 +41,15 @@ class FilterBank(list):
   def __init__(self, filters=()):
     list.__init__(self, filters)
     self._sections = None
+    self._sections_of = None
     self.freqs = None
     self.rate = None
 
   def sections(self):
     """Channels -> sections -> ``(b, a)``: the table handed to ``alz_plan_create``."""
-    if self._sections is None or len(self._sections) != len(self):
+    ids = tuple(id(f) for f in self)                   # the cache follows any mutation of the list
+    if self._sections is None or self._sections_of != ids:
+      self._sections_of = ids
       table = []
       for f in self:
         if isinstance(f, CascadeFilter):
@@ -82,9 +85,14 @@ class FilterBank(list):
       x = x.unsqueeze(0)
     if state is None:
       state = self.new_state(x.shape[0])
-    if state.n_streams != x.shape[0]:
-      raise ValueError("state was created for %d streams, x has %d" % (state.n_streams, x.shape[0]))
+    self._check_state(state, x.shape[0], db)
     return db.apply(x, state.tensor, out=out)
+
+  def _check_state(self, state, n_streams, db):
+    if state.n_streams != n_streams:
+      raise ValueError("state was created for %d streams, x has %d" % (state.n_streams, n_streams))
+    if state.tensor.numel() != max(1, db.plan.state_doubles(n_streams)) or state.tensor.device != db.device:
+      raise ValueError("state belongs to another bank or device")
 
   def freq_response(self, freqs):
     """Complex128 ndarray ``[C, n]``: every channel's response on the grid ``freqs`` (rad/sample),
@@ -99,7 +107,9 @@ class FilterBank(list):
     x = np.asarray(x, dtype=np.float32)
     state_ptr = None
     if state is not None:
-      if state.n_streams != (1 if x.ndim == 1 else x.shape[0]):
-        raise ValueError("state / input stream count mismatch")
+      self._check_state(state, 1 if x.ndim == 1 else x.shape[0], db)
+      # alz_apply_f32_host runs on private streams ordered after the legacy default stream only: whatever
+      # produced the state on torch's current stream (new_state, a previous apply) must be complete
+      _engine.torch_mod().cuda.current_stream(db.device).synchronize()
       state_ptr = state.tensor.data_ptr()
     return db.plan.apply_host(x, out, state_ptr)

@@ -61,6 +61,8 @@ struct AlzTileArgs {
   int C;            // channels of the whole bank (output row index = s*C + c)
   int vec_in;       // 1: x rows are 16-byte aligned (16 B cp.async), 0: 4 B cp.async
   int vec_out;      // 1: y rows are 16-byte aligned (st.v4), 0: scalar stores
+  int exp;          // ALZ_EXP (profiling experiments, TMA engine; results are garbage): 1 = load only the first
+                    // tile group and refilter it, 2 = no tile stores
 };
 
 __device__ __forceinline__ void alz_cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {

@@ -121,7 +121,8 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   for (int i = 0; i < ntiles; ++i) {
     const int j = NG == 1 ? (i & 1) : (i & (NG - 1));   // buffer of tile i
     const int t0 = i * ALZ_TT;
-    if (lane == 0) {
+    const bool skip_load = (a.exp & 1) && i >= NG;
+    if (lane == 0 && !skip_load) {
       if (NG == 1) {
         if (i + 1 < ntiles) {
           // The other buffer was the source of the TMA store of tile i-1: wait until the store has
@@ -139,13 +140,14 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
         }
       }
     }
-    alz_mbar_wait(mbar0 + 8 * j, (NG == 1 ? (i >> 1) : (i >> lg)) & 1);   // tile i has landed (async proxy writes visible after the wait)
+    if (!((a.exp & 1) && i >= (NG == 1 ? 2 : NG)))
+      alz_mbar_wait(mbar0 + 8 * j, (NG == 1 ? (i >> 1) : (i >> lg)) & 1);   // tile i has landed (async proxy writes visible after the wait)
     const int nvalid = i < nfull ? ALZ_TT : (int)(tlen - t0);
     core.tile(myrow + j * (ALZ_TMA_TILE_BYTES / 4), swz, nvalid, t0);
     alz_fence_async_smem();                          // my generic-proxy writes -> visible to the TMA store
     __syncwarp();
     const bool last = i + 1 == ntiles;
-    if (lane == 0) {
+    if (lane == 0 && !(a.exp & 2)) {
       if (NG == 1) {
         if (!(tail_by_lanes && last)) alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + j * ALZ_TMA_TILE_BYTES);   // ragged last tile: stored after the loop
         alz_bulk_commit();

@@ -54,6 +54,7 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, const void* bl
     ng = alzi_env_int("ALZ_TMA_PAIRED", ng);     // 0/1 = prefetch pipeline, 2 / 4 = tile groups
     if (ng != 2 && ng != 4) ng = 1;
     ta.paired = ng;
+    ta.exp = alzi_env_int("ALZ_EXP", 0);
     const size_t smem = ALZ_TMA_SMEM_FOR(ng);
     const long long per_sm = std::min<long long>(kWarpsPerSmTma, (228 * 1024) / (long long)(smem + 1024));
     const long long slots = (long long)p->sm_count * per_sm;

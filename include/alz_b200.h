@@ -174,6 +174,18 @@ int32_t alz_apply_f32(const alz_plan* plan, const float* x_dev, float* y_dev,
                       int64_t x_stride, int64_t y_stride, void* cuda_stream);
 
 /*
+ * Same as alz_apply_f32 with an explicit distance (in elements) between the output rows of
+ * consecutive STREAMS: row (s, c) starts at y_dev + s * y_stream_stride + c * y_stride.  Lets a
+ * plan that holds a SLICE of a bank's channels (channel-sharded multi-GPU, audiolazy_b200/parallel.py)
+ * write its rows straight into the full y[S][C_total][T] tensor -- local, or a peer GPU's over
+ * NVLink -- with y_dev offset to its first channel.  y_stream_stride >= n_channels * y_stride.
+ * The time-parallel evaluation of few long streams is not used on this entry.
+ */
+int32_t alz_apply_f32_ex(const alz_plan* plan, const float* x_dev, float* y_dev, double* state_dev,
+                         int64_t n_streams, int64_t n_samples, int64_t x_stride, int64_t y_stride,
+                         int64_t y_stream_stride, void* cuda_stream);
+
+/*
  * Time-varying coefficients (reference lazy_filters.py:200-216: Stream-valued b_k / a_k are
  * advanced once per input sample).  For a single-channel GENERIC plan, alz_plan_taps() lists
  * the taps in the order of the coefficient table: delay[i], is_den[i] (1 for feedback taps).
@@ -189,13 +201,24 @@ int32_t alz_apply_tv_f32(const alz_plan* plan, const float* x_dev, float* y_dev,
 /*
  * Same with HOST buffers: host->device copy of x, the kernel, device->host copy
  * of y, chunked over streams and pipelined on internal CUDA streams.  The host
- * buffers may be pageable or pinned (pinned is faster).  state_dev may be NULL
- * (zero initial state, discarded afterwards).  Synchronous: y_host is complete on
- * return.
+ * buffers may be pageable or pinned (pinned is faster; alz_host_alloc below).  state_dev may
+ * be NULL (zero initial state, discarded afterwards).  Synchronous: y_host is complete on
+ * return.  ORDERING: the copies and kernels run on private non-blocking streams that are ordered
+ * after the LEGACY DEFAULT stream at entry; a state_dev produced on any other stream must be
+ * complete (synchronised) before the call.
  */
 int32_t alz_apply_f32_host(const alz_plan* plan, const float* x_host, float* y_host,
                            double* state_dev, int64_t n_streams, int64_t n_samples,
                            int64_t x_stride, int64_t y_stride);
+
+/*
+ * Pinned host buffers for alz_apply_f32_host, placed on the NUMA node of CUDA device `device`
+ * (< 0: the current device) so that several GPUs can run their PCIe copies at full rate at the same
+ * time.  *numa_node (may be NULL) receives the node the pages were bound to, or -1 when the
+ * topology is not visible.  Free with alz_host_free.
+ */
+int32_t alz_host_alloc(void** out, int64_t bytes, int32_t device, int32_t* numa_node);
+int32_t alz_host_free(void* ptr);
 
 /*
  * ParallelFilter reduction: out[s][t] = ((y[s][0][t] + y[s][1][t]) + ...) over

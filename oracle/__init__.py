@@ -198,3 +198,62 @@ def py_cascade(sections, seq, memory=None, zero=0.0):
   for b, a in sections:
     data = py_section(b, a, data, memory=memory, zero=zero)
   return data
+
+
+# --------------------------------------------------------------------------------------
+# compiled-source Python restatement: what CPython costs the reference per sample
+# --------------------------------------------------------------------------------------
+def py_compiled_section(b, a, zero=0.0):
+  """A generator FUNCTION ``gen(seq)`` for one section, built the way the reference builds its
+  evaluator (``lazy_filters.py:197-260``): the difference equation is written out as ONE Python
+  expression over local delay variables, compiled with ``exec``, and the histories are shifted
+  by plain assignments -- so that its per-sample cost in CPython is the reference's. Same term
+  order, +-1 elision, zero dropping and ``/ a0`` on the sum as :func:`py_section`."""
+  b = [float(v) for v in b]
+  a = [float(v) for v in a]
+  while len(b) > 1 and b[-1] == 0:
+    b.pop()
+  while len(a) > 1 and a[-1] == 0:
+    a.pop()
+  if a[0] == 0:
+    raise ZeroDivisionError("Invalid filter gain")
+  terms = []
+  for k, c in enumerate(b):
+    if c == 1:
+      terms.append("x%d" % k)
+    elif c == -1:
+      terms.append("-x%d" % k)
+    elif c != 0:
+      terms.append("%r * x%d" % (c, k))
+  for k, c in enumerate(a):
+    if k == 0 or c == 0:
+      continue
+    terms.append("y%d" % k if c == -1 else ("-y%d" % k if c == 1 else "-%r * y%d" % (c, k)))
+  body = ["def gen(seq):"]
+  if not terms:
+    body += ["  for x0 in seq:", "    yield %r" % zero]
+  else:
+    expr = " + ".join(terms)
+    if a[0] == -1:
+      expr = "-(%s)" % expr
+    elif a[0] != 1:
+      expr = "(%s) / %r" % (expr, a[0])
+    for k in range(1, len(a)):
+      body.append("  y%d = %r" % (k, zero))
+    for k in range(1, len(b)):
+      body.append("  x%d = %r" % (k, zero))
+    body += ["  for x0 in seq:", "    y0 = " + expr, "    yield y0"]
+    body += ["    y%d = y%d" % (k, k - 1) for k in range(len(a) - 1, 0, -1)]
+    body += ["    x%d = x%d" % (k, k - 1) for k in range(len(b) - 1, 0, -1)]
+  scope = {}
+  exec("\n".join(body), scope)
+  return scope["gen"]
+
+
+def py_compiled_cascade(sections, seq, zero=0.0):
+  """Nested generators, one per section, consumed lazily (``CascadeFilter.__call__``,
+  ``lazy_filters.py:988-990``). Returns the outermost generator."""
+  data = iter(seq)
+  for b, a in sections:
+    data = py_compiled_section(b, a, zero)(data)
+  return data

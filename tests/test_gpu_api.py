@@ -149,17 +149,46 @@ def test_lazy_pump_and_batch_state(ab):
   assert rel_err(whole.cpu().numpy(), oracle.bank_apply(x.cpu().numpy(), bank.sections())) <= TOL
 
 
-def test_two_gpu_channel_sharding(ab):
+def test_nccl_sharding_parity_under_torchrun(ab):
+  """Both multi-GPU partitionings on real NCCL, launched the way the driver launches bench.py: channel-sharded
+  (overlapped broadcast pipeline, in-place all-gather, fused peer-memory store) and stream-sharded (scatter), every
+  result bit-identical to the single-GPU bank (tools/nccl_check.py). Needs >= 2 GPUs."""
+  import subprocess
+  import sys
   import torch
   if torch.cuda.device_count() < 2:
     pytest.skip("needs 2 GPUs")
-  # one process, two devices: the same plan machinery on another device index
+  from conftest import ROOT
+  import os
+  env = dict(os.environ, ALZ_CHECK_S="256", ALZ_CHECK_T="4096")
+  out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "nccl_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env)
+  assert out.returncode == 0 and "PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_sharded_bank_single_process(ab):
+  """world size 1 (no process group): the sharded wrapper degenerates to the bank itself; state=None is a fresh
+  state on every call, as FilterBank.apply."""
+  import torch
+  from audiolazy_b200.parallel import ShardedBank
   bank = ab.gammatone_bank(freqs=ab.erb_space(n=8), strategy="slaney")
-  x = np.stack([signal(60 + i, 2048) for i in range(33)])
-  with torch.cuda.device(1):
-    y1 = bank.apply(torch.from_numpy(x).cuda()).cpu().numpy()
-  y0 = bank.apply(torch.from_numpy(x).cuda()).cpu().numpy()
-  assert np.array_equal(y0, y1)
+  x = torch.from_numpy(np.stack([signal(60 + i, 2048) for i in range(33)])).cuda()
+  want = bank.apply(x)
+  for mode in ("streams", "channels"):
+    sb = ShardedBank(bank, mode=mode)
+    assert torch.equal(sb.apply(x), want) and torch.equal(sb.apply(x), want)
+    assert torch.equal(sb.gather_output(sb.apply(x)), want)
+  sb = ShardedBank(bank, mode="channels")
+  buf = sb.alloc_gather(33, 2048)
+  sb.gather_output_into(want, buf)
+  assert torch.equal(buf[0], want)
+  st = bank.new_state(33)
+  a = sb.apply(x[:, :1000].contiguous(), state=st)
+  b = sb.apply(x[:, 1000:].contiguous(), state=st)
+  assert torch.equal(torch.cat([a, b], dim=2), want)
+  with pytest.raises(ValueError):                      # a state of another bank must not reach the kernel
+    bank.apply(x, state=ab.gammatone_bank(freqs=ab.erb_space(n=4), strategy="slaney").new_state(33))
 
 
 def test_callers_of_the_path(ab, vectors):

@@ -269,14 +269,43 @@ def test_gain_modes(gpu, designs, monkeypatch):
   bank = designs["bank_slaney"]
   x = np.stack([signal(0, 8000), signal(7, 8000)])
   want = oracle.bank_apply(x, bank)
-  fast = gpu.capi.Plan(bank)
-  assert fast.monic and fast.fp64_ops == 12
+  fast = gpu.capi.Plan(bank, exact=True)              # exact: every channel on the float64 tier
+  assert fast.monic and fast.fp64_ops == 12 and fast.n_fp32_channels == 0
   assert rel_err(gpu.run(fast, x), want) <= 2.5e-7
   monkeypatch.setenv("ALZ_EXACT_GAIN", "1")
-  exact = gpu.capi.Plan(bank)
+  exact = gpu.capi.Plan(bank, exact=True)
   monkeypatch.delenv("ALZ_EXACT_GAIN")
   assert exact.fp64_ops == 13
   assert rel_err(gpu.run(exact, x), want) <= 6.5e-8   # = float32 rounding of the float64 result
+
+
+@pytest.mark.parametrize("name", ["slaney", "klapuri", "sampled"])
+def test_precision_tiers(gpu, designs, monkeypatch, name):
+  """Channels whose float32 evaluation the plan-time probe measured at <= 2.5e-6 run their recurrence in
+  float32 (tier 1), the others in float64 (tier 0).  The bar is 1e-5: tier-1 channels must keep a 3x margin
+  on signals the probe has not seen, tier-0 channels are float32 roundings of the float64 result."""
+  bank = designs["bank_" + name]
+  plan = gpu.capi.Plan(bank)
+  tier, probe = plan.tiers()
+  assert plan.n_fp32_channels == int(tier.sum()) and 8 <= plan.n_fp32_channels <= 48
+  assert abs(plan.tier_tol - 2.5e-6) < 1e-12
+  assert np.all(probe[tier == 1] <= plan.tier_tol) and np.all(probe[tier == 0] > plan.tier_tol)
+  assert not tier[:16].any()                           # poles next to z = 1: never float32
+  x = np.stack([signal(0, 8000), signal(7, 8000), signal(8, 8000), signal(21, 8000)])
+  want = oracle.bank_apply(x, bank)
+  y = gpu.run(plan, x)
+  err = np.max(np.max(np.abs(y - want), axis=-1) / np.max(np.abs(want), axis=-1), axis=0)      # per channel
+  assert np.all(err[tier == 0] <= 2.5e-7)
+  assert np.all(err[tier == 1] <= TOL / 3), err[tier == 1].max()
+  exact = gpu.capi.Plan(bank, exact=True)
+  assert exact.n_fp32_channels == 0 and not exact.tiers()[0].any()
+  ye = gpu.run(exact, x)
+  assert rel_err(ye, want) <= 2.5e-7
+  assert np.array_equal(ye[:, tier == 0], y[:, tier == 0])        # the float64 channels do not depend on the tiering
+  monkeypatch.setenv("ALZ_NO_FP32_TIER", "1")
+  assert gpu.capi.Plan(bank).n_fp32_channels == 0
+  monkeypatch.delenv("ALZ_NO_FP32_TIER")
+  assert np.array_equal(gpu.run(plan, x, splits=[1, 1, 30, 33, 935, 7000]), y)   # block splitting stays bit-exact in both tiers
 
 
 def test_structurally_zero_taps_are_skipped(gpu, designs, monkeypatch):

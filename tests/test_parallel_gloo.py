@@ -56,6 +56,13 @@ def _worker(rank, world, port, out):
     assert y_local.shape == (S, sb.c_hi - sb.c_lo, T)
     assert torch.equal(y_local, want[:, sb.c_lo:sb.c_hi])
     assert torch.equal(sb.gather_output(y_local), want)
+    # in-place gather: ONE all_gather_into_tensor into the rank-major [world][S][C/world][T] buffer
+    assert sb.even_channels
+    buf = torch.empty((world, S, 6 // world, T), dtype=torch.float32)
+    sb.gather_output_into(y_local.contiguous(), buf)
+    assert torch.equal(buf.permute(1, 0, 2, 3).reshape(S, 6, T), want)
+    # two independent batches through the sharded bank: state=None starts from zero EVERY call (as FilterBank.apply)
+    assert torch.equal(sb.apply(x), y_local)
 
     # streams mode: scatter rows from rank 0, no collective in apply
     sb = ShardedBank(bank, mode="streams", compute=compute)
@@ -65,6 +72,13 @@ def _worker(rank, world, port, out):
     y_local = sb.apply(x_loc)
     assert torch.equal(y_local, want[lo:hi])
     assert torch.equal(sb.gather_output(y_local), want)
+    # equal shares: one scatter straight into the destination rows
+    x6 = torch.cat([x_all, x_all[:1]])                     # 6 streams, 3 per rank
+    dst = torch.empty((3, T), dtype=torch.float32)
+    sb.scatter_input_into(x6 if rank == 0 else None, dst, src=0)
+    assert torch.equal(dst, x6[3 * rank: 3 * rank + 3])
+    y6 = sb.apply(dst)
+    assert torch.equal(sb.gather_output(y6), torch.from_numpy(oracle.bank_apply_f32(x6.numpy(), full_sections)))
     out.put((rank, "ok"))
   except Exception as exc:  # pragma: no cover
     out.put((rank, repr(exc)))
