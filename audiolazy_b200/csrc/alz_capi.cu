@@ -408,6 +408,75 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
     }
     p->tile_group = env_int("ALZ_TILE_GROUP", 2);
     if (p->tile_group != 1 && p->tile_group != 2 && p->tile_group != 4) p->tile_group = 2;
+  } else if (Kmax == 1 && !(flags & ALZ_PLAN_FORCE_GENERIC) && C * 32 <= kCoefLarge && !env_int("ALZ_NO_WINDOW", 0)) {
+    // ---- window: one section per channel, dense near taps in registers + prefetched far taps (alz_window.cuh) ----
+    p->kind = ALZ_KIND_GENERIC;
+    p->window = true;
+    p->K = 1;
+    p->NB = nbmax;
+    p->monic = 0;
+    int near_x = 0, near_y = 0, maxd_x = 0, maxd_y = 0;
+    std::vector<int> far_x, far_y;                    // union over the channels of the taps with delay >= 16
+    for (int c = 0; c < C; ++c) {
+      if (secs[c].empty()) continue;
+      const Sec& s = secs[c][0];
+      for (size_t d = 1; d < s.b.size(); ++d)
+        if (s.b[d] != 0.0) {
+          maxd_x = std::max(maxd_x, (int)d);
+          if (d < 16) near_x = std::max(near_x, (int)d);
+          else if (std::find(far_x.begin(), far_x.end(), (int)d) == far_x.end()) far_x.push_back((int)d);
+        }
+      for (size_t d = 1; d < s.a.size(); ++d)
+        if (s.a[d] != 0.0) {
+          maxd_y = std::max(maxd_y, (int)d);
+          if (d < 16) near_y = std::max(near_y, (int)d);
+          else if (std::find(far_y.begin(), far_y.end(), (int)d) == far_y.end()) far_y.push_back((int)d);
+        }
+    }
+    std::sort(far_x.begin(), far_x.end());
+    std::sort(far_y.begin(), far_y.end());
+    auto slots_of = [](int nearest) { return nearest == 0 ? 0 : (nearest <= 3 ? 4 : 16); };
+    auto pow2 = [](int n) { int q = 1; while (q < n) q <<= 1; return q; };
+    p->win_mx = slots_of(near_x);
+    p->win_my = slots_of(near_y);
+    p->win_nfx = (int)far_x.size();
+    p->win_nfy = (int)far_y.size();
+    int slot = 1;                                     // slot 0: absolute sample count
+    p->win_xwin = slot; slot += p->win_mx ? p->win_mx - 1 : 0;
+    p->win_ywin = slot; slot += p->win_my ? p->win_my - 1 : 0;
+    if (!far_x.empty()) { p->win_xbase = slot; p->win_xmask = pow2(far_x.back() + 16) - 1; slot += p->win_xmask + 1; }
+    if (!far_y.empty()) { p->win_ybase = slot; p->win_ymask = pow2(far_y.back() + 16) - 1; slot += p->win_ymask + 1; }
+    p->xd = maxd_x; p->yd = maxd_y;
+    p->state_doubles = slot;
+    p->fp64_ops = 1 + (p->win_mx ? p->win_mx - 1 : 0) + (p->win_my ? p->win_my - 1 : 0) + p->win_nfx + p->win_nfy;
+    p->win_far_delay = far_x;
+    p->win_far_delay.insert(p->win_far_delay.end(), far_y.begin(), far_y.end());
+    p->h_tab.assign((size_t)C * 32, 0.0);             // [C][b0..b15, -a1..-a15, pad]
+    std::vector<double> fcoef(std::max<size_t>(1, p->win_far_delay.size()) * C, 0.0);
+    for (int c = 0; c < C; ++c) {
+      double* rec = p->h_tab.data() + (size_t)c * 32;
+      if (secs[c].empty()) { rec[0] = 1.0; continue; }   // empty cascade: identity
+      const Sec& s = secs[c][0];
+      for (size_t d = 0; d < s.b.size() && d < 16; ++d) rec[d] = s.b[d];
+      for (size_t d = 1; d < s.a.size() && d < 16; ++d) rec[16 + d - 1] = -s.a[d];
+      for (size_t f = 0; f < far_x.size(); ++f) fcoef[f * C + c] = (size_t)far_x[f] < s.b.size() ? s.b[far_x[f]] : 0.0;
+      for (size_t f = 0; f < far_y.size(); ++f) fcoef[(far_x.size() + f) * C + c] = (size_t)far_y[f] < s.a.size() ? -s.a[far_y[f]] : 0.0;
+    }
+    p->coef_small = C * 32 <= 64;
+    p->win_block = calloc(1, alzi_window_block_bytes(p->coef_small));
+    if (!p->win_block) { alz_plan_destroy(p); return fail(ALZ_ERR_NOMEM, "out of host memory"); }
+    if (!design_only) {
+      const size_t nf = std::max<size_t>(1, p->win_far_delay.size());
+      std::vector<int> fd(nf, 16);
+      std::copy(p->win_far_delay.begin(), p->win_far_delay.end(), fd.begin());
+      cudaError_t e = cudaMalloc(&p->d_far_delay, nf * sizeof(int));
+      if (e == cudaSuccess) e = cudaMemcpy(p->d_far_delay, fd.data(), nf * sizeof(int), cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMalloc(&p->d_far_coef, fcoef.size() * sizeof(double));
+      if (e == cudaSuccess) e = cudaMemcpy(p->d_far_coef, fcoef.data(), fcoef.size() * sizeof(double), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) { alz_plan_destroy(p); return fail(ALZ_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e)); }
+    }
+    alzi_window_block_fill(p->win_block, p->coef_small, p->win_nfx, p->win_nfy, p->win_xbase, p->win_xmask, p->win_ybase,
+                           p->win_ymask, p->win_xwin, p->win_ywin, C, p->d_far_delay, p->d_far_coef, p->h_tab.data());
   } else {
     // ---- generic: union tap structure per section --------------------------------
     const int K = Kmax;
@@ -488,6 +557,7 @@ void alz_plan_destroy(alz_plan* p) {
   if (!p) return;
   if (p->device < 0) {   // design-only: host tables only
     for (auto& ch : p->chunks) free(ch.block);
+    free(p->win_block);
     delete p;
     return;
   }
@@ -503,6 +573,9 @@ void alz_plan_destroy(alz_plan* p) {
     }
   }
   for (auto& ch : p->chunks) free(ch.block);
+  free(p->win_block);
+  cudaFree(p->d_far_delay);
+  cudaFree(p->d_far_coef);
   cudaFree(p->d_coef);
   cudaFree(p->d_sec);
   cudaFree(p->d_tap_delay);
@@ -591,6 +664,19 @@ int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double
           proto[(size_t)(base + nx + j) * C + c] = yv * sc_out;
         }
       }
+  } else if (p->window) {
+    for (int c = 0; c < C; ++c) {
+      for (int j = 0; j < p->xd; ++j) {                 // entry j = delay j+1
+        const double xv = xinit ? xinit[(size_t)c * p->xd + j] : 0.0;
+        if (j + 1 < p->win_mx) proto[(size_t)(p->win_xwin + j) * C + c] = xv;
+        if (p->win_xmask >= 0) proto[(size_t)(p->win_xbase + ((-(j + 1)) & p->win_xmask)) * C + c] = xv;
+      }
+      for (int j = 0; j < p->yd; ++j) {
+        const double yv = yinit ? yinit[(size_t)c * p->yd + j] : 0.0;
+        if (j + 1 < p->win_my) proto[(size_t)(p->win_ywin + j) * C + c] = yv;
+        if (p->win_ymask >= 0) proto[(size_t)(p->win_ybase + ((-(j + 1)) & p->win_ymask)) * C + c] = yv;
+      }
+    }
   } else {
     for (int c = 0; c < C; ++c)
       for (int k = 0; k < K; ++k) {
@@ -621,7 +707,9 @@ static int apply_launch(const alz_plan* p, AlzTileArgs ta, double* state, long l
                         const double* tv, long long tv_stride) {
   ta.state = state;
   ta.sstride = sstride;
-  return p->kind == ALZ_KIND_BIQUAD ? launch_biquad(p, ta, st) : launch_generic(p, ta, st, tv, tv_stride);
+  if (p->kind == ALZ_KIND_BIQUAD) return launch_biquad(p, ta, st);
+  if (p->window) return alzi_launch_window(p, ta, st);
+  return launch_generic(p, ta, st, tv, tv_stride);
 }
 
 // ---- time-parallel evaluation of FEW long streams ------------------------------------------
@@ -797,7 +885,7 @@ int32_t alz_apply_f32_ex(const alz_plan* p, const float* x, float* y, double* st
 
 int32_t alz_plan_taps(const alz_plan* p, int32_t* delay, int32_t* is_den, int32_t cap) {
   if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
-  if (p->kind != ALZ_KIND_GENERIC) return fail(ALZ_ERR_UNSUPPORTED, "tap list exists only for generic plans");
+  if (p->kind != ALZ_KIND_GENERIC || p->window) return fail(ALZ_ERR_UNSUPPORTED, "tap list exists only for plans built with ALZ_PLAN_FORCE_GENERIC");
   const int n = (int)p->h_tap_delay.size();
   for (int i = 0; i < n && i < cap; ++i) {
     if (delay) delay[i] = p->h_tap_delay[i];
@@ -809,8 +897,8 @@ int32_t alz_plan_taps(const alz_plan* p, int32_t* delay, int32_t* is_den, int32_
 int32_t alz_apply_tv_f32(const alz_plan* p, const float* x, float* y, double* state, int64_t S, int64_t T,
                          int64_t xs, int64_t ys, const double* coef_dev, int64_t coef_stride, void* cuda_stream) {
   if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
-  if (p->kind != ALZ_KIND_GENERIC || p->C != 1)
-    return fail(ALZ_ERR_UNSUPPORTED, "time-varying coefficients need a single-channel generic plan (alz_plan_create_ex)");
+  if (p->kind != ALZ_KIND_GENERIC || p->C != 1 || p->window)
+    return fail(ALZ_ERR_UNSUPPORTED, "time-varying coefficients need a single-channel generic plan (alz_plan_create_ex with ALZ_PLAN_FORCE_GENERIC)");
   if (S < 0 || T < 0) return fail(ALZ_ERR_INVALID, "negative size");
   if (S == 0 || T == 0) return ALZ_OK;
   if (!x || !y || !state || !coef_dev) return fail(ALZ_ERR_INVALID, "null buffer");

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -55,6 +56,16 @@ struct alz_plan {
   bool coef_small = false;     // kernel-parameter block size (kCoefSmall / kCoefLarge doubles)
   struct Chunk { void* block; int npos; };
   std::vector<Chunk> chunks;   // biquad: pre-built AlzBiquadArgs<NCOEF> blocks, <= NCOEF / stride positions each
+  // generic plans of ONE section per channel run on the window kernels (alz_window.cuh)
+  bool window = false;
+  int win_mx = 0, win_my = 0;           // near-window slots per history (0, 4, 16)
+  int win_xwin = 0, win_ywin = 0;       // state slots of the near windows
+  int win_xbase = 0, win_xmask = -1, win_ybase = 0, win_ymask = -1;   // far rings
+  std::vector<int> win_far_delay;       // numerator taps first
+  int win_nfx = 0, win_nfy = 0;
+  void* win_block = nullptr;            // host AlzWindowArgs<NCOEF>
+  int* d_far_delay = nullptr;
+  double* d_far_coef = nullptr;
   // device tables
   double* d_coef = nullptr;
   AlzGenSection* d_sec = nullptr;
@@ -87,6 +98,11 @@ int alzi_launch_biquad_k6(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 int alzi_launch_biquad_k8(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 int alzi_launch_headfir_k1(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 int alzi_launch_headfir_k4(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+
+int alzi_launch_window(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+size_t alzi_window_block_bytes(bool small);
+void alzi_window_block_fill(void* blk, bool small, int n_far_x, int n_far_y, int xbase, int xmask, int ybase, int ymask, int xwin,
+                            int ywin, int C, const int* far_delay, const double* far_coef, const double* coef);
 
 // Plan-time tier probe (host): runs channel records through the SAME core arithmetic in float64
 // and float32 on probe signals, returns the float32 tier's error relative to the row peak.

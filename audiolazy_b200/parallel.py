@@ -220,7 +220,7 @@ class BroadcastPipeline(object):
     self.sb, self.x, self.y, self.state, self.src = sharded, x_blocks, y, state, src
     self.torch = torch
     dev = y.device
-    self.side = torch.cuda.Stream(device=dev)
+    self.side = torch.cuda.Stream(device=dev, priority=-1)
     self.bc_done = [torch.cuda.Event(), torch.cuda.Event()]
     self.i = 0
     self.primed = False

@@ -341,7 +341,10 @@ def extras(torch, dev, args, peak):
     lpc_a = [1.0] + (rng.uniform(-1, 1, 12) * 0.5 ** np.arange(1, 13)).tolist()
     gen["lpc12_analysis_fir"] = device_record(torch, dev, _capi.Plan([[(lpc_a, [1.0])]]), S * 16, Tn, steps=3, warm=1)
     gen["lpc12_synthesis_allpole"] = device_record(torch, dev, _capi.Plan([[([1.0], lpc_a)]]), S * 16, Tn, steps=3, warm=1)
-    gen["note"] = "single-channel plans over %d streams x %d samples (8 B per sample); kernels: generic family" % (S * 16, Tn)
+    gen["biquad_kernel_reference"] = device_record(torch, dev, _capi.Plan([[([1.0, 0.5, 0.2], [1.0, -0.3, 0.1])]]), S * 16, Tn, steps=3, warm=1)
+    gen["note"] = "single-channel plans over %d streams x %d samples (8 B per sample); kernels: window family (one section of " \
+                  "any order / sparsity: dense near taps in registers, far taps prefetched from the state ring); " \
+                  "biquad_kernel_reference = one float64 biquad on the biquad kernel at the same shape" % (S * 16, Tn)
     out["generic"] = gen
   except Exception as exc:
     out["generic"] = {"error": repr(exc)}
@@ -388,7 +391,11 @@ def run_ours(args):
   if distributed:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not mix with the JSON line on stdout
-    dist.init_process_group("nccl", device_id=dev)
+    try:                                                      # NCCL kernels on a high-priority stream: a broadcast issued under a
+      opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # running bank kernel gets SM slots as soon as CTAs retire
+      dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    except Exception:
+      dist.init_process_group("nccl", device_id=dev)
 
   def barrier():
     if distributed:

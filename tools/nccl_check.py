@@ -19,7 +19,10 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-dist.init_process_group("nccl", device_id=dev)
+try:
+  dist.init_process_group("nccl", device_id=dev, pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
+except Exception:
+  dist.init_process_group("nccl", device_id=dev)
 bank = ab.gammatone_bank(strategy="slaney")
 C = len(bank)
 S, T = int(os.environ.get("ALZ_CHECK_S", 1024)), int(os.environ.get("ALZ_CHECK_T", 8192))
