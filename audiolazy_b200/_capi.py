@@ -25,6 +25,7 @@ KIND_GENERIC = 2
 PLAN_FORCE_GENERIC = 1
 PLAN_EXACT = 2
 PLAN_DESIGN_ONLY = 4
+PLAN_SEQUENTIAL = 8
 
 #: every symbol include/alz_b200.h declares (tests check the library exports them all)
 SYMBOLS = (
@@ -140,12 +141,12 @@ def pack_sections(bank):
 class Plan(object):
   """A compiled bank of cascades living on the current CUDA device."""
 
-  def __init__(self, bank, force_generic=False, exact=False, design_only=False):
+  def __init__(self, bank, force_generic=False, exact=False, design_only=False, sequential=False):
     L = lib()
     coef, desc, C, KM = pack_sections(bank)
     handle = ctypes.c_void_p()
     flags = (PLAN_FORCE_GENERIC if force_generic else 0) | (PLAN_EXACT if exact else 0) | \
-            (PLAN_DESIGN_ONLY if design_only else 0)
+            (PLAN_DESIGN_ONLY if design_only else 0) | (PLAN_SEQUENTIAL if sequential else 0)
     _check(L.alz_plan_create_ex(coef.ctypes.data, desc.ctypes.data, C, KM, flags, ctypes.byref(handle)))
     self._h = handle
     info = PlanInfo()

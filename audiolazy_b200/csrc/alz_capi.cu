@@ -109,7 +109,22 @@ bool alzi_make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap*
   if (ta.T >= (1ll << 31) || ta.S >= (1ll << 31)) return false;
   if ((unsigned long long)ta.xs * 4 >= (1ull << 40) || (unsigned long long)ta.ysS * 4 >= (1ull << 40)) return false;
   if (ta.ysS & 3) return false;
-  const cuuint32_t estr[3] = {1, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  if (ta.vP > 0) {
+    // virtual streams: row v = chunk v % P of real stream v / P; T = chunk length, xs / ys / ysS = the REAL strides
+    const cuuint64_t P = (cuuint64_t)ta.vP, Sreal = (cuuint64_t)(ta.S / ta.vP);
+    const cuuint64_t xdims[3] = {(cuuint64_t)ta.T, P, Sreal};
+    const cuuint64_t xstr[2] = {(cuuint64_t)ta.T * 4, (cuuint64_t)ta.xs * 4};
+    const cuuint32_t xbox[3] = {32, 32, 1};
+    if (enc(tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ta.x, xdims, xstr, xbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    const cuuint64_t ydims[4] = {(cuuint64_t)ta.T, P, (cuuint64_t)ta.C, Sreal};
+    const cuuint64_t ystr[3] = {(cuuint64_t)ta.T * 4, (cuuint64_t)ta.ys * 4, (cuuint64_t)ta.ysS * 4};
+    const cuuint32_t ybox[4] = {32, 32, 1, 1};
+    return enc(tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ta.y, ydims, ystr, ybox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)ta.T, (cuuint64_t)ta.S};
     const cuuint64_t strides[1] = {(cuuint64_t)ta.xs * 4};
@@ -245,6 +260,7 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
   if (!p) return fail(ALZ_ERR_NOMEM, "out of host memory");
   p->C = C;
   p->device = dev;
+  p->sequential = (flags & ALZ_PLAN_SEQUENTIAL) != 0;
   if (design_only || cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || p->sm_count <= 0) {
     cudaGetLastError();
     p->sm_count = 148;
@@ -573,6 +589,7 @@ void alz_plan_destroy(alz_plan* p) {
     }
   }
   for (auto& ch : p->chunks) free(ch.block);
+  for (auto& e : p->m_cache) { cudaFree(e.M); cudaEventDestroy(e.ready); }
   free(p->win_block);
   cudaFree(p->d_far_delay);
   cudaFree(p->d_far_coef);
@@ -731,22 +748,24 @@ static __global__ void alz_unit_state_kernel(double* m, int d, int C) {   // m[s
   m[i] = (rest % d == j) ? 1.0 : 0.0;
 }
 
-// One WARP per channel (d <= 32): lane j owns state slot j, keeps row j of M in registers and
+// One WARP per (channel, stream) (d <= 32): lane j owns state slot j, keeps row j of M in registers and
 // the running state is exchanged with shuffles; F of the next chunk is prefetched.
+// F / init: [slot][C][S][P] (virtual stream v = s * P + p); user state: [slot][C][Stot_user], stream offset applied by the caller.
 static __global__ void __launch_bounds__(32) alz_chunk_scan_kernel(const double* __restrict__ F, double* __restrict__ init,
                                                             const double* __restrict__ M, double* user_state,
                                                             long long user_stride, long long user_stot, int d, int C,
-                                                            long long P) {
+                                                            long long S, long long P) {
   const int c = blockIdx.x, j = threadIdx.x;
+  const long long sidx = blockIdx.y;
   const bool on = j < d;
   double mrow[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) mrow[i] = (on && i < d) ? M[(long long)j * d * C + (long long)c * d + i] : 0.0;
-  double* us = user_state + (long long)(on ? j : 0) * user_stride + (long long)c * user_stot;
+  double* us = user_state + (long long)(on ? j : 0) * user_stride + (long long)c * user_stot + sidx;
   double cur = on ? *us : 0.0;
-  const long long pc = P * C;
-  const double* Fj = F + (long long)(on ? j : 0) * pc + (long long)c * P;
-  double* Ij = init + (long long)(on ? j : 0) * pc + (long long)c * P;
+  const long long slot_stride = (long long)C * S * P;
+  const double* Fj = F + (long long)(on ? j : 0) * slot_stride + ((long long)c * S + sidx) * P;
+  double* Ij = init + (long long)(on ? j : 0) * slot_stride + ((long long)c * S + sidx) * P;
   double f_next = (on && P > 0) ? Fj[0] : 0.0;
   for (long long p = 0; p < P; ++p) {
     const double f = f_next;
@@ -765,74 +784,125 @@ static __global__ void __launch_bounds__(32) alz_chunk_scan_kernel(const double*
   if (on) *us = cur;
 }
 
-static bool chunked_applies(const alz_plan* p, long long S, long long T) {
-  if (p->kind != ALZ_KIND_BIQUAD || env_int("ALZ_NO_TIME_PARALLEL", 0)) return false;
-  if (S > 32 || T < 65536) return false;   // one warp row of streams: sequential would leave the machine ~2% occupied
-  return (long long)p->C * ((S + 31) / 32) <= 256 && p->state_doubles <= 32;
+static int apply_impl(const alz_plan* p, const float* x, float* y, double* state, long long sstride, long long S,
+                      long long T, long long xs, long long ys, cudaStream_t st, const double* tv, long long tv_stride, long long ysS);
+static int apply_plain(const alz_plan* p, const float* x, float* y, double* state, long long sstride, long long S,
+                       long long T, long long xs, long long ys, cudaStream_t st) {
+  return apply_impl(p, x, y, state, sstride, S, T, xs, ys, st, nullptr, 0, 0);
+}
+
+// Time-parallel evaluation pays when the plain launch (one warp per channel and 32 streams, serial in time)
+// would leave most of the machine idle: few streams, long blocks.  P chunks per stream (a multiple of 32, so that
+// a warp's 32 virtual streams are chunks of ONE real stream: 3-D / 4-D tensor maps), L samples each.
+static bool chunk_geometry(const alz_plan* p, const float* x, const float* y, long long S, long long T, long long xs,
+                           long long ys, long long* P_out, long long* L_out) {
+  if (p->kind != ALZ_KIND_BIQUAD || p->sequential || env_int("ALZ_NO_TIME_PARALLEL", 0)) return false;
+  if (T < std::max(2048, env_int("ALZ_TIME_PARALLEL_MIN", 16384)) || p->state_doubles > 32) return false;
+  if (T >= (1ll << 31) || S > 65535) return false;
+  const long long slots = (long long)p->sm_count * 24;
+  const long long warps = (long long)p->C * ((S + 31) / 32);
+  if (warps * 2 > slots) return false;             // the plain launch already fills half of the machine
+  // cost model (measured on B200, tools/time_small.py): a lone warp advances one sample per ~36 ns (12 FP64 ops per
+  // channel-sample); the machine as a whole does ~1.2e12 channel-samples/s and the chunked evaluation runs 2 passes + extras
+  const double work = std::max(1, p->fp64_ops) / 12.0;
+  const double t_seq = (double)T * 36e-9 * work;
+  const double t_par = 2.6 * (double)S * (double)T * p->C * work / 1.2e12 + 1e-4;
+  if (t_par > 0.8 * t_seq) return false;
+  long long Pmax = (2 * slots * 32 + p->C * S - 1) / (p->C * S);   // virtual warps ~ 2 x resident slots
+  Pmax = (Pmax + 31) / 32 * 32;
+  if (Pmax > 1024) Pmax = 1024;                    // the scan over the chunks of a stream is serial (~200 cycles per chunk)
+  if (Pmax * 256 > T) Pmax = T / 256 / 32 * 32;    // chunks of at least 256 samples
+  if (Pmax < 32) return false;
+  // chunks are whole tiles (L % 32 == 0), so T mod 32 P samples are left over for a sequential tail: among the chunk
+  // counts near the target take the one with the shortest tail
+  long long P = Pmax, best_tail = T % (32 * Pmax);
+  for (long long q = Pmax - 32; q >= 32 && q * 2 >= Pmax; q -= 32) {
+    const long long tail = T % (32 * q);
+    if (tail < best_tail) { best_tail = tail; P = q; }
+  }
+  const long long L = T / P / 32 * 32;
+  if (L < 256) return false;
+  *P_out = P;
+  *L_out = L;
+  return true;
 }
 
 static int apply_chunked(const alz_plan* p, const float* x, float* y, double* state, long long sstride, long long S,
-                         long long T, long long xs, long long ys, cudaStream_t st) {
+                         long long T, long long xs, long long ys, long long P, long long L, cudaStream_t st) {
   const int C = p->C, d = p->state_doubles;
-  // chunk count: enough virtual streams to give every SM sub-partition a few warps, at most
-  // 1024 (the scan over chunks is serial: ~200 cycles per chunk)
-  long long want = 2ll * 148 * 4 * 32 / C;
-  if (want > 1024) want = 1024;
-  if (want < 256) want = 256;
-  long long L = (T / want + 31) / 32 * 32;
-  if (L < 256) L = 256;
-  const long long P = T / L, Tmain = P * L;
-  const size_t nstate = (size_t)d * P * C;
+  const long long Tmain = P * L, V = S * P;        // V virtual streams
+  const size_t nstate = (size_t)d * V * C;
   keep_async_pool();
   double *Z1 = nullptr, *Z2 = nullptr, *M = nullptr;
   float *xz = nullptr, *ydum = nullptr;
   ALZ_CUDA(cudaMallocAsync((void**)&Z1, nstate * 8, st));
   ALZ_CUDA(cudaMallocAsync((void**)&Z2, nstate * 8, st));
-  ALZ_CUDA(cudaMallocAsync((void**)&M, (size_t)d * d * C * 8, st));
-  ALZ_CUDA(cudaMallocAsync((void**)&xz, (size_t)d * L * 4, st));
-  ALZ_CUDA(cudaMallocAsync((void**)&ydum, (size_t)d * C * L * 4, st));
-  ALZ_CUDA(cudaMemsetAsync(xz, 0, (size_t)d * L * 4, st));
+  ALZ_CUDA(cudaMemsetAsync(Z1, 0, nstate * 8, st));
   int rc = ALZ_OK;
-  {   // basis run (once: M does not depend on the stream)
+  // M = A^L depends on the plan and the chunk length only: computed once per (plan, L), kept on the device
+  alz_plan* pm = const_cast<alz_plan*>(p);
+  cudaEvent_t m_ready = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(pm->m_mu);
+    for (auto& e : pm->m_cache)
+      if (e.L == L) { M = e.M; m_ready = e.ready; }
+  }
+  if (M) {
+    ALZ_CUDA(cudaStreamWaitEvent(st, m_ready, 0));
+  } else {   // basis run: L zero samples from each unit state -> M = A^L, per channel (it does not depend on the stream)
+    ALZ_CUDA(cudaMalloc((void**)&M, (size_t)d * d * C * 8));
+    ALZ_CUDA(cudaMallocAsync((void**)&xz, (size_t)d * L * 4, st));
+    ALZ_CUDA(cudaMallocAsync((void**)&ydum, (size_t)d * C * L * 4, st));
+    ALZ_CUDA(cudaMemsetAsync(xz, 0, (size_t)d * L * 4, st));
     const long long n = (long long)d * d * C;
     alz_unit_state_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(M, d, C);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     AlzTileArgs tb{};
     tb.x = xz; tb.y = ydum; tb.S = d; tb.T = L; tb.xs = L; tb.ys = L; tb.ysS = (long long)C * L; tb.C = C; tb.Stot = d;
     tb.vec_in = tb.vec_out = 1;
+    tb.exp = 2;                                                                 // its outputs are not needed: no tile stores
     rc = apply_launch(p, tb, M, (long long)d * C, st, nullptr, 0);
+    cudaFreeAsync(xz, st); cudaFreeAsync(ydum, st);
+    ALZ_CUDA(cudaEventCreateWithFlags(&m_ready, cudaEventDisableTiming));
+    ALZ_CUDA(cudaEventRecord(m_ready, st));
+    std::lock_guard<std::mutex> lock(pm->m_mu);
+    if (pm->m_cache.size() >= 8) {                 // bounded: drop the oldest entry (its users were ordered before this point on their streams)
+      cudaStreamSynchronize(st);
+      cudaFree(pm->m_cache.front().M);
+      cudaEventDestroy(pm->m_cache.front().ready);
+      pm->m_cache.erase(pm->m_cache.begin());
+    }
+    pm->m_cache.push_back({L, M, m_ready});
   }
-  for (long long s = 0; s < S && rc == ALZ_OK; ++s) {
-    AlzTileArgs ta{};
-    ta.x = x + s * xs; ta.y = y + s * C * ys; ta.S = P; ta.T = L; ta.xs = L; ta.ys = ys; ta.ysS = L; ta.C = C; ta.Stot = P;
-    ta.vec_in = (((uintptr_t)ta.x & 15) == 0) ? 1 : 0;
-    ta.vec_out = (((uintptr_t)ta.y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
-    ALZ_CUDA(cudaMemsetAsync(Z1, 0, nstate * 8, st));
-    rc = apply_launch(p, ta, Z1, P * C, st, nullptr, 0);                       // pass 1: zero-state chunks
-    if (rc != ALZ_OK) break;
-    alz_chunk_scan_kernel<<<C, 32, 0, st>>>(Z1, Z2, M, state + s, sstride, sstride / C, d, C, P);
+  AlzTileArgs ta{};
+  ta.x = x; ta.y = y; ta.S = V; ta.T = L; ta.xs = xs; ta.ys = ys; ta.ysS = (long long)C * ys; ta.C = C; ta.Stot = V;
+  ta.vec_in = (((uintptr_t)x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;          // L is a multiple of 32: chunk starts keep the alignment
+  ta.vec_out = (((uintptr_t)y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
+  ta.vP = (int)P;
+  if (rc == ALZ_OK) {
+    ta.exp = 2;                                                                 // pass 1: zero-state chunks, only the final states matter
+    rc = apply_launch(p, ta, Z1, V * C, st, nullptr, 0);
+  }
+  if (rc == ALZ_OK) {
+    alz_chunk_scan_kernel<<<dim3((unsigned)C, (unsigned)S), 32, 0, st>>>(Z1, Z2, M, state, sstride, sstride / C, d, C, S, P);
     ALZ_CUDA(cudaGetLastError());
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    rc = apply_launch(p, ta, Z2, P * C, st, nullptr, 0);                       // pass 2: true initial states
-    if (rc != ALZ_OK) break;
-    if (T > Tmain) {                                                           // ragged tail, sequentially
-      AlzTileArgs tt{};
-      tt.x = x + s * xs + Tmain; tt.y = y + s * C * ys + Tmain; tt.S = 1; tt.T = T - Tmain; tt.xs = xs; tt.ys = ys;
-      tt.ysS = (long long)C * ys; tt.C = C; tt.Stot = sstride / C;
-      tt.vec_in = (((uintptr_t)tt.x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
-      tt.vec_out = (((uintptr_t)tt.y & 15) == 0 && (ys & 3) == 0) ? 1 : 0;
-      rc = apply_launch(p, tt, state + s, sstride, st, nullptr, 0);
-    }
+    ta.exp = 0;
+    rc = apply_launch(p, ta, Z2, V * C, st, nullptr, 0);                        // pass 2: every chunk from its true initial state
   }
-  cudaFreeAsync(Z1, st); cudaFreeAsync(Z2, st); cudaFreeAsync(M, st); cudaFreeAsync(xz, st); cudaFreeAsync(ydum, st);
+  cudaFreeAsync(Z1, st); cudaFreeAsync(Z2, st);
+  if (rc == ALZ_OK && T > Tmain)                                                // left-over samples of all streams: the same decision again
+    rc = apply_plain(p, x + Tmain, y + Tmain, state, sstride, S, T - Tmain, xs, ys, st);
   return rc;
 }
 
 static int apply_impl(const alz_plan* p, const float* x, float* y, double* state, long long sstride, long long S,
-                      long long T, long long xs, long long ys, cudaStream_t st, const double* tv = nullptr,
-                      long long tv_stride = 0, long long ysS = 0) {
+                      long long T, long long xs, long long ys, cudaStream_t st, const double* tv,
+                      long long tv_stride, long long ysS) {
   if (ysS == 0) ysS = (long long)p->C * ys;
-  if (!tv && ysS == (long long)p->C * ys && chunked_applies(p, S, T)) return apply_chunked(p, x, y, state, sstride, S, T, xs, ys, st);
+  long long P = 0, L = 0;
+  if (!tv && ysS == (long long)p->C * ys && chunk_geometry(p, x, y, S, T, xs, ys, &P, &L))
+    return apply_chunked(p, x, y, state, sstride, S, T, xs, ys, P, L, st);
   AlzTileArgs ta{};
   ta.T = T; ta.xs = xs; ta.ys = ys; ta.ysS = ysS; ta.C = p->C;
   ta.Stot = sstride / p->C;
@@ -861,7 +931,7 @@ int32_t alz_apply_f32(const alz_plan* p, const float* x, float* y, double* state
   int cur = -1;
   ALZ_CUDA(cudaGetDevice(&cur));
   if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
-  const int rc = apply_impl(p, x, y, state, (long long)S * p->C, S, T, xs, ys, (cudaStream_t)cuda_stream);
+  const int rc = apply_plain(p, x, y, state, (long long)S * p->C, S, T, xs, ys, (cudaStream_t)cuda_stream);
   if (cur != p->device) cudaSetDevice(cur);
   return rc;
 }
@@ -906,7 +976,7 @@ int32_t alz_apply_tv_f32(const alz_plan* p, const float* x, float* y, double* st
   int cur = -1;
   ALZ_CUDA(cudaGetDevice(&cur));
   if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
-  const int rc = apply_impl(p, x, y, state, (long long)S, S, T, xs, ys, (cudaStream_t)cuda_stream, coef_dev, coef_stride);
+  const int rc = apply_impl(p, x, y, state, (long long)S, S, T, xs, ys, (cudaStream_t)cuda_stream, coef_dev, coef_stride, 0);
   if (cur != p->device) cudaSetDevice(cur);
   return rc;
 }
@@ -984,7 +1054,7 @@ int32_t alz_apply_f32_host(const alz_plan* cp, const float* xh, float* yh, doubl
       if (prev) { cudaStreamWaitEvent(st, prev, 0); cudaEventDestroy(prev); prev = nullptr; }
       cudaError_t e = cudaMemcpy2DAsync(hp.dx[b], Tp * 4, xh + s0 * xs + t0, xs * 4, nt * 4, n, cudaMemcpyHostToDevice, st);
       if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
-      rc = apply_impl(p, hp.dx[b], hp.dy[b], st_buf + s0, (long long)S * C, n, nt, Tp, Tp, st);
+      rc = apply_plain(p, hp.dx[b], hp.dy[b], st_buf + s0, (long long)S * C, n, nt, Tp, Tp, st);
       if (rc != ALZ_OK) break;
       if (t0 + Tc < T) {
         cudaEventCreateWithFlags(&prev, cudaEventDisableTiming);

@@ -61,6 +61,8 @@ struct AlzTileArgs {
   int C;            // channels of the whole bank (output row index = s*C + c)
   int vec_in;       // 1: x rows are 16-byte aligned (16 B cp.async), 0: 4 B cp.async
   int vec_out;      // 1: y rows are 16-byte aligned (st.v4), 0: scalar stores
+  int vP;           // > 0: VIRTUAL streams (time-parallel evaluation, alz_capi.cu): row v of this launch is chunk v % vP
+                    // of real stream v / vP; x / y are reached through 3-D / 4-D tensor maps (TMA engine only, vP % 32 == 0)
   int exp;          // ALZ_EXP (profiling experiments, TMA engine; results are garbage): 1 = load only the first
                     // tile group and refilter it, 2 = no tile stores
 };
@@ -82,16 +84,18 @@ __device__ __forceinline__ void alz_st_v4(float* p, float4 v) {
 }
 
 // Bring tile t0 of the 32 input rows of stream group `s0` into `buf` (zero filled beyond S / T).
-__device__ __forceinline__ void alz_issue_tile(const AlzTileArgs& a, float* buf, long long s0, long long t0, int lane,
-                                               bool lean) {
+// xg / xstr: address of row 0 of this stream group and the distance between its rows (real streams: a.x + s0 * xs, xs;
+// virtual streams: the 32 rows are consecutive chunks of one real stream, distance = the chunk length).
+__device__ __forceinline__ void alz_issue_tile(const AlzTileArgs& a, float* buf, const float* xg, long long xstr, long long s0,
+                                               long long t0, int lane, bool lean) {
   const int sub = lane >> 3, col = (lane & 7) << 2;
   if (lean) {   // full tile, full group, aligned: 8 unpredicated 16-byte copies per lane
-    const float* src = a.x + (s0 + sub) * a.xs + t0 + col;
+    const float* src = xg + sub * xstr + t0 + col;
     float* dst = buf + sub * ALZ_PITCH + col;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       alz_cp_async16(dst, src, 16);
-      src += 4 * a.xs;
+      src += 4 * xstr;
       dst += 4 * ALZ_PITCH;
     }
   } else if (a.vec_in) {
@@ -101,14 +105,14 @@ __device__ __forceinline__ void alz_issue_tile(const AlzTileArgs& a, float* buf,
       const long long left = a.T - (t0 + col);
       int n = left >= 4 ? 4 : (left > 0 ? (int)left : 0);
       if (s0 + row >= a.S) n = 0;
-      const float* src = n ? a.x + (s0 + row) * a.xs + t0 + col : a.x;
+      const float* src = n ? xg + row * xstr + t0 + col : a.x;
       alz_cp_async16(buf + row * ALZ_PITCH + col, src, n * 4);
     }
   } else {
 #pragma unroll 1
     for (int row = 0; row < 32; ++row) {
       const bool in = (t0 + lane) < a.T && (s0 + row) < a.S;
-      const float* src = in ? a.x + (s0 + row) * a.xs + t0 + lane : a.x;
+      const float* src = in ? xg + row * xstr + t0 + lane : a.x;
       alz_cp_async4(buf + row * ALZ_PITCH + lane, src, in ? 4 : 0);
     }
   }
@@ -143,12 +147,17 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
   const bool lean_out = a.vec_out && full_group;
   const int sub = lane >> 3, col = (lane & 7) << 2;
   float* const myrow0 = smem + lane * ALZ_PITCH;
-  const long long ystep = 4ll * a.ysS;
+  // rows of this stream group in x and y (virtual streams: consecutive chunks of ONE real stream, vP % 32 == 0)
+  const float* const xg = a.vP > 0 ? a.x + (s0 / a.vP) * a.xs + (s0 % a.vP) * a.T : a.x + s0 * a.xs;
+  const long long xstr = a.vP > 0 ? a.T : a.xs;
+  float* const yg = (a.vP > 0 ? a.y + (s0 / a.vP) * a.ysS + (s0 % a.vP) * a.T : a.y + s0 * a.ysS) + c * a.ys;
+  const long long ystr = a.vP > 0 ? a.T : a.ysS;
+  const long long ystep = 4ll * ystr;
 
   // prologue: tiles 0 and 1 in flight
-  alz_issue_tile(a, smem, s0, 0, lane, lean_in && nfull > 0);
+  alz_issue_tile(a, smem, xg, xstr, s0, 0, lane, lean_in && nfull > 0);
   alz_cp_commit();
-  if (ntiles > 1) alz_issue_tile(a, smem + 32 * ALZ_PITCH, s0, ALZ_TT, lane, lean_in && nfull > 1);
+  if (ntiles > 1) alz_issue_tile(a, smem + 32 * ALZ_PITCH, xg, xstr, s0, ALZ_TT, lane, lean_in && nfull > 1);
   alz_cp_commit();
 
   for (long long i = 0; i < ntiles; ++i) {
@@ -160,8 +169,10 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
     core.tile(myrow0 + (i & 1) * (32 * ALZ_PITCH), 0, nvalid, t0);
     __syncwarp();
 
-    if (lean_out && i < nfull) {
-      float* dst = a.y + (s0 + sub) * a.ysS + c * a.ys + t0 + col;
+    if (a.y == nullptr) {
+      // ALZ_EXP & 2 / zero-state pass of the time-parallel evaluation: only the final states are wanted
+    } else if (lean_out && i < nfull) {
+      float* dst = yg + sub * ystr + t0 + col;
       const float* src = buf + sub * ALZ_PITCH + col;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -175,7 +186,7 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
         const int row = it * 4 + sub;
         if (s0 + row < a.S && col < nvalid) {
           const float4 v = *reinterpret_cast<const float4*>(buf + row * ALZ_PITCH + col);
-          float* dst = a.y + (s0 + row) * a.ysS + c * a.ys + t0 + col;
+          float* dst = yg + row * ystr + t0 + col;
           if (a.vec_out && col + 4 <= nvalid) {
             alz_st_v4(dst, v);
           } else {
@@ -188,7 +199,7 @@ __device__ __forceinline__ void alz_run_warp(const AlzTileArgs& a, const CoreArg
       }
     }
     __syncwarp();   // the buffer has been read by every lane: refill it with tile i+2
-    if (i + 2 < ntiles) alz_issue_tile(a, buf, s0, t0 + 2 * ALZ_TT, lane, lean_in && i + 2 < nfull);
+    if (i + 2 < ntiles) alz_issue_tile(a, buf, xg, xstr, s0, t0 + 2 * ALZ_TT, lane, lean_in && i + 2 < nfull);
     alz_cp_commit();
   }
   alz_cp_wait<0>();

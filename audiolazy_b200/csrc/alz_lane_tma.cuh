@@ -48,6 +48,23 @@ __device__ __forceinline__ void alz_tma_store_3d(const CUtensorMap* map, int c0,
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];\n"
                ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
 }
+__device__ __forceinline__ void alz_tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned mbar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void alz_tma_store_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3, unsigned src) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n"
+               ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src) : "memory");
+}
+// tile load / store of stream group s0 (virtual streams: chunk p0 = s0 % vP of real stream s0 / vP)
+__device__ __forceinline__ void alz_tile_load(const AlzTileArgs& a, unsigned dst, const CUtensorMap* tmx, int t, long long s0, unsigned mbar) {
+  if (a.vP > 0) alz_tma_load_3d(dst, tmx, t, (int)(s0 % a.vP), (int)(s0 / a.vP), mbar);
+  else alz_tma_load_2d(dst, tmx, t, (int)s0, mbar);
+}
+__device__ __forceinline__ void alz_tile_store(const AlzTileArgs& a, const CUtensorMap* tmy, int t, int c, long long s0, unsigned src) {
+  if (a.vP > 0) alz_tma_store_4d(tmy, t, (int)(s0 % a.vP), c, (int)(s0 / a.vP), src);
+  else alz_tma_store_3d(tmy, t, c, (int)s0, src);
+}
 __device__ __forceinline__ void alz_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void alz_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void alz_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
@@ -116,7 +133,7 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   const int lg = NG >= 4 ? 2 : (NG >= 2 ? 1 : 0);
   if (lane == 0 && NG == 1) {   // tile 0 in flight
     alz_mbar_expect_tx(mbar0, ALZ_TMA_TILE_BYTES);
-    alz_tma_load_2d(tile0, tmx, tb, (int)s0, mbar0);
+    alz_tile_load(a, tile0, tmx, tb, s0, mbar0);
   }
   for (int i = 0; i < ntiles; ++i) {
     const int j = NG == 1 ? (i & 1) : (i & (NG - 1));   // buffer of tile i
@@ -129,14 +146,14 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
           // finished READING it (it was issued a whole barrier-wait ago, so this normally does not block).
           if (i >= 1) alz_bulk_wait_read0();
           alz_mbar_expect_tx(mbar0 + 8 * (j ^ 1), ALZ_TMA_TILE_BYTES);
-          alz_tma_load_2d(tile0 + (j ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, (int)s0, mbar0 + 8 * (j ^ 1));
+          alz_tile_load(a, tile0 + (j ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, s0, mbar0 + 8 * (j ^ 1));
         }
       } else if (j == 0) {
         if (i > 0) alz_bulk_wait_read0();
         const int n = ntiles - i < NG ? ntiles - i : NG;
         for (int jj = 0; jj < n; ++jj) {
           alz_mbar_expect_tx(mbar0 + 8 * jj, ALZ_TMA_TILE_BYTES);
-          alz_tma_load_2d(tile0 + jj * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + jj * ALZ_TT, (int)s0, mbar0 + 8 * jj);
+          alz_tile_load(a, tile0 + jj * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + jj * ALZ_TT, s0, mbar0 + 8 * jj);
         }
       }
     }
@@ -149,12 +166,12 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
     const bool last = i + 1 == ntiles;
     if (lane == 0 && !(a.exp & 2)) {
       if (NG == 1) {
-        if (!(tail_by_lanes && last)) alz_tma_store_3d(tmy, tb + t0, c, (int)s0, tile0 + j * ALZ_TMA_TILE_BYTES);   // ragged last tile: stored after the loop
+        if (!(tail_by_lanes && last)) alz_tile_store(a, tmy, tb + t0, c, s0, tile0 + j * ALZ_TMA_TILE_BYTES);   // ragged last tile: stored after the loop
         alz_bulk_commit();
       } else if (j == NG - 1 || last) {
         for (int jj = 0; jj <= j; ++jj)
           if (!(tail_by_lanes && last && jj == j))
-            alz_tma_store_3d(tmy, tb + t0 - (j - jj) * ALZ_TT, c, (int)s0, tile0 + jj * ALZ_TMA_TILE_BYTES);
+            alz_tile_store(a, tmy, tb + t0 - (j - jj) * ALZ_TT, c, s0, tile0 + jj * ALZ_TMA_TILE_BYTES);
         alz_bulk_commit();
       }
     }

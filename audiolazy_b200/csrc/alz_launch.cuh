@@ -54,12 +54,12 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, const void* bl
     ng = alzi_env_int("ALZ_TMA_PAIRED", ng);     // 0/1 = prefetch pipeline, 2 / 4 = tile groups
     if (ng != 2 && ng != 4) ng = 1;
     ta.paired = ng;
-    ta.exp = alzi_env_int("ALZ_EXP", 0);
+    ta.exp |= alzi_env_int("ALZ_EXP", 0);
     const size_t smem = ALZ_TMA_SMEM_FOR(ng);
     const long long per_sm = std::min<long long>(kWarpsPerSmTma, (228 * 1024) / (long long)(smem + 1024));
     const long long slots = (long long)p->sm_count * per_sm;
     long long nseg = 1;
-    if (warps > slots && warps < 8 * slots && ta.T >= 2048 && !alzi_env_int("ALZ_NO_SEGMENT", 0)) {
+    if (ta.vP == 0 && warps > slots && warps < 8 * slots && ta.T >= 2048 && !alzi_env_int("ALZ_NO_SEGMENT", 0)) {
       const long long waves = std::max(1, alzi_env_int("ALZ_SEG_WAVES", 16)), min_len = std::max(32, alzi_env_int("ALZ_SEG_MIN", 1024));
       nseg = std::min((waves * slots + warps - 1) / warps, ta.T / min_len);
       const long long quantum = 32ll * ng;     // whole tile groups per segment
@@ -87,6 +87,7 @@ static int launch_biquad_chunk(const alz_plan* p, AlzTileArgs ta, const void* bl
     if (ta.sync) cudaFreeAsync(ta.sync, st);
     ALZ_CUDA(e);
   } else {
+    if (ta.exp & 2) ta.y = nullptr;   // cp.async engine: "no tile stores" is expressed by a null output (see alz_run_warp)
     auto kern = alz_biquad_kernel<K, NB, MONIC, NCOEF, NB0, ZMASK>;
     void* args[2] = {(void*)&ta, const_cast<void*>(block)};
     ALZ_CUDA(cudaLaunchKernel((const void*)kern, dim3((unsigned)npos, (unsigned)groups), dim3(32), args, ALZ_WARP_SMEM, st));

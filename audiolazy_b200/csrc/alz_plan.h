@@ -53,6 +53,7 @@ struct alz_plan {
   double tier_tol = 0.0;       // measured-error threshold the tier decision used
   int probe_len = 8192;        // samples per probe signal of the tier decision
   int tile_group = 2;          // TMA engine: tiles moved together by launches that fill the machine (1, 2, 4)
+  bool sequential = false;     // ALZ_PLAN_SEQUENTIAL: never evaluate time-parallel (bit-reproducible blocking)
   bool coef_small = false;     // kernel-parameter block size (kCoefSmall / kCoefLarge doubles)
   struct Chunk { void* block; int npos; };
   std::vector<Chunk> chunks;   // biquad: pre-built AlzBiquadArgs<NCOEF> blocks, <= NCOEF / stride positions each
@@ -85,6 +86,9 @@ struct alz_plan {
   double* d_fr_coef = nullptr;
   int fr_K = 0;
   int* d_fr_desc = nullptr;
+  struct MEntry { long long L; double* M; cudaEvent_t ready; };
+  std::mutex m_mu;               // guards m_cache (NOT host_mu: alz_apply_f32_host holds that one across its launches)
+  std::vector<MEntry> m_cache;   // time-parallel evaluation: chunk transition matrices A^L per chunk length (device)
   std::mutex host_mu;
   AlzHostPipe pipe;
 };

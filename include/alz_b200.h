@@ -119,6 +119,9 @@ int32_t alz_plan_create(const double* coef, const int32_t* section_desc,
  * (works on a host without a GPU); only alz_plan_info_get / alz_plan_tiers / alz_plan_history /
  * alz_plan_state_doubles / alz_plan_destroy accept such a plan, every compute entry fails. */
 #define ALZ_PLAN_DESIGN_ONLY 4
+/* ALZ_PLAN_SEQUENTIAL: never use the time-parallel evaluation (see alz_apply_f32): every call is
+ * evaluated sample by sample, so ANY blocking of a stream gives the same bits. */
+#define ALZ_PLAN_SEQUENTIAL 8
 int32_t alz_plan_create_ex(const double* coef, const int32_t* section_desc, int32_t n_channels,
                            int32_t max_sections, int32_t flags, alz_plan** out);
 
@@ -163,10 +166,13 @@ int32_t alz_plan_history(const alz_plan* plan, int32_t* xd, int32_t* yd);
  * x_stride elements.  y_dev: [n_streams * n_channels] rows (stream-major,
  * channel-minor) of n_samples float32, row stride y_stride elements.
  * state_dev: in/out, carries every recurrence across blocks, so that
- * apply(block0) ; apply(block1) == apply(block0 ++ block1) bit for bit.  (Exception: calls
- * with <= 32 streams of >= 65536 samples are evaluated time-parallel -- zero-state chunks,
- * transition matrices, scan, replay -- and agree with the sequential result to float64
- * rounding of the chunk states, ~1e-6 relative at worst; ALZ_NO_TIME_PARALLEL=1 disables it.)
+ * apply(block0) ; apply(block1) == apply(block0 ++ block1) bit for bit.  (Exception: a call
+ * whose sequential launch would leave more than half of the GPU idle -- n_channels * ceil(n_streams / 32)
+ * warps < half the resident warp slots -- with n_samples >= 16384 (ALZ_TIME_PARALLEL_MIN) is
+ * evaluated time-parallel: every stream is cut into chunks, all chunks run from a zero state, the
+ * chunk transition matrices are scanned, all chunks run again from their true initial states.  The
+ * result agrees with the sequential one to float64 rounding of the chunk states, ~1e-6 relative
+ * at worst.  A plan created with ALZ_PLAN_SEQUENTIAL, or ALZ_NO_TIME_PARALLEL=1, never does this.)
  * Asynchronous on `cuda_stream`.
  */
 int32_t alz_apply_f32(const alz_plan* plan, const float* x_dev, float* y_dev,

@@ -242,7 +242,7 @@ def test_time_parallel_path(gpu, designs, monkeypatch):
     # state carry: a long block (chunked) followed by short ones (sequential) == one shot
     split = gpu.run(plan, x, xinit=xi, yinit=yi, splits=[131072 + 5, 1000, 200077 - 131077 - 1000])
     assert rel_err(split, fast) <= 3e-6
-  # up to one warp row of streams (32) takes this path, stream by stream
+  # a dozen streams: one batch
   x = np.stack([signal(300 + i, 70000) for i in range(12)])
   plan = gpu.capi.Plan(designs["bank_slaney"][:16])
   fast = gpu.run(plan, x)
@@ -250,6 +250,27 @@ def test_time_parallel_path(gpu, designs, monkeypatch):
   slow = gpu.run(plan, x)
   monkeypatch.delenv("ALZ_NO_TIME_PARALLEL")
   assert rel_err(fast, slow) <= 3e-6
+
+
+@pytest.mark.parametrize("S,T,C", [(33, 40000, 64), (100, 16384 + 37, 16), (256, 65536, 8), (1000, 20000, 1), (5, 300001, 64)])
+def test_time_parallel_batches_all_streams(gpu, designs, monkeypatch, S, T, C):
+  """33 ... ~1000 streams that would leave most of the GPU idle are evaluated time-parallel in ONE batch (virtual
+  streams = (stream, chunk) pairs, 3-D / 4-D tensor maps; the cp.async engine when rows are not 16-byte aligned):
+  against the sequential evaluation and, on a few rows, against the oracle; state carried into a following block."""
+  bank = designs["bank_slaney"][:C]
+  plan = gpu.capi.Plan(bank)
+  rng = np.random.default_rng(S)
+  x = rng.uniform(-1, 1, (S, T)).astype(np.float32)
+  fast = gpu.run(plan, x, splits=[T - 1000, 1000])       # long block: time-parallel; short block: sequential, from its state
+  monkeypatch.setenv("ALZ_NO_TIME_PARALLEL", "1")
+  slow = gpu.run(plan, x)
+  monkeypatch.delenv("ALZ_NO_TIME_PARALLEL")
+  assert rel_err(fast, slow) <= 3e-6
+  rows = [0, S // 2, S - 1]
+  assert rel_err(fast[rows][:, :, :30000], oracle.bank_apply(x[rows][:, :30000], bank)) <= TOL
+  seq = gpu.capi.Plan(bank, sequential=True)             # ALZ_PLAN_SEQUENTIAL: any blocking, same bits
+  assert np.array_equal(gpu.run(seq, x), slow)
+  assert np.array_equal(gpu.run(seq, x, splits=[T - 1000, 1000]), slow)
 
 
 def test_host_path_time_segments(gpu, designs):
