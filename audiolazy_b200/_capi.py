@@ -26,12 +26,13 @@ PLAN_FORCE_GENERIC = 1
 PLAN_EXACT = 2
 PLAN_DESIGN_ONLY = 4
 PLAN_SEQUENTIAL = 8
+PLAN_PARALLEL = 16
 
 #: every symbol include/alz_b200.h declares (tests check the library exports them all)
 SYMBOLS = (
   "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_create_ex",
   "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32", "alz_plan_tiers", "alz_apply_f32_ex", "alz_host_alloc",
-  "alz_host_free",
+  "alz_host_free", "alz_apply_sum_f32",
   "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
   "alz_apply_f32_host", "alz_sum_channels_f32", "alz_freq_response_f64", "alz_launch_count",
 )
@@ -95,6 +96,8 @@ def lib():
   L.alz_apply_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
   L.alz_apply_f32_ex.restype = i32
   L.alz_apply_f32_ex.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp]
+  L.alz_apply_sum_f32.restype = i32
+  L.alz_apply_sum_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
   L.alz_host_alloc.restype = i32
   L.alz_host_alloc.argtypes = [ctypes.POINTER(vp), i64, i32, ctypes.POINTER(i32)]
   L.alz_host_free.restype = i32
@@ -141,12 +144,12 @@ def pack_sections(bank):
 class Plan(object):
   """A compiled bank of cascades living on the current CUDA device."""
 
-  def __init__(self, bank, force_generic=False, exact=False, design_only=False, sequential=False):
+  def __init__(self, bank, force_generic=False, exact=False, design_only=False, sequential=False, parallel=False):
     L = lib()
     coef, desc, C, KM = pack_sections(bank)
     handle = ctypes.c_void_p()
     flags = (PLAN_FORCE_GENERIC if force_generic else 0) | (PLAN_EXACT if exact else 0) | \
-            (PLAN_DESIGN_ONLY if design_only else 0) | (PLAN_SEQUENTIAL if sequential else 0)
+            (PLAN_DESIGN_ONLY if design_only else 0) | (PLAN_SEQUENTIAL if sequential else 0) | (PLAN_PARALLEL if parallel else 0)
     _check(L.alz_plan_create_ex(coef.ctypes.data, desc.ctypes.data, C, KM, flags, ctypes.byref(handle)))
     self._h = handle
     info = PlanInfo()
@@ -186,6 +189,12 @@ class Plan(object):
   def apply(self, x_ptr, y_ptr, state_ptr, n_streams, n_samples, x_stride, y_stride, stream=0):
     _check(lib().alz_apply_f32(self._h, x_ptr, y_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),
                                int(y_stride), stream))
+
+  def apply_sum(self, x_ptr, out_ptr, state_ptr, n_streams, n_samples, x_stride, out_stride, stream=0):
+    """ParallelFilter in one kernel (plans created with ``parallel=True``); raises :class:`NativeError`
+    (ALZ_ERR_UNSUPPORTED) for unaligned rows or non-biquad members."""
+    _check(lib().alz_apply_sum_f32(self._h, x_ptr, out_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),
+                                   int(out_stride), stream))
 
   def tiers(self):
     """``(tier int32[C], probe_err float64[C])``: precision tier of every channel (0 float64, 1 float32) and the

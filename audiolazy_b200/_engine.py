@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import itertools as it
 import threading
+from array import array
 from collections import deque
 
 import numpy as np
@@ -39,11 +40,12 @@ class DeviceBank(object):
   """A plan (bank of cascades) bound to the current CUDA device plus the torch-side
   helpers to allocate state / output and launch on torch's current stream."""
 
-  def __init__(self, bank_sections):
+  def __init__(self, bank_sections, parallel=False):
     torch = torch_mod()
     self.device = torch.device("cuda", torch.cuda.current_device())
     _capi.set_device(self.device.index)
-    self.plan = _capi.Plan(bank_sections)
+    self.plan = _capi.Plan(bank_sections, parallel=parallel)
+    self.parallel = parallel
     self.n_channels = self.plan.n_channels
     self._sections = bank_sections
 
@@ -103,6 +105,29 @@ class DeviceBank(object):
     self.plan.freq_response(w.data_ptr(), out.data_ptr(), w.numel(), torch.cuda.current_stream(self.device).cuda_stream)
     return torch.view_as_complex(out)
 
+  def apply_sum(self, x, state):
+    """ParallelFilter: ``x[S, T]`` -> ``out[S, T]`` = the left-associated sum of every channel's output. One kernel
+    (float64 accumulation, channel outputs never reach memory) when the plan allows it, else bank launch + channel sum."""
+    torch = torch_mod()
+    if x.dim() == 1:
+      x = x.unsqueeze(0)
+    S, T = x.shape
+    if self.parallel and self.plan.kind == _capi.KIND_BIQUAD and self.plan.num_taps <= 3:
+      # rows padded to 16 bytes: the fused kernel moves its tiles with TMA
+      Tp = (T + 3) & ~3
+      xp = x if (T == Tp and x.is_contiguous() and x.data_ptr() % 16 == 0) else None
+      if xp is None:
+        xp = torch.zeros((S, Tp), dtype=torch.float32, device=x.device)
+        xp[:, :T] = x
+      out = torch.empty((S, Tp), dtype=torch.float32, device=x.device)
+      try:
+        self.plan.apply_sum(xp.data_ptr(), out.data_ptr(), state.data_ptr(), S, T, Tp, Tp,
+                            torch.cuda.current_stream(x.device).cuda_stream)
+        return out[:, :T]
+      except _capi.NativeError:
+        pass                              # more channels than one parameter block, ...: the two-kernel path below
+    return self.sum_channels(self.apply(x, state))
+
   def sum_channels(self, y):
     torch = torch_mod()
     S, C, T = y.shape
@@ -111,17 +136,27 @@ class DeviceBank(object):
     return out
 
 
-def device_bank(bank_sections):
-  """Cached :class:`DeviceBank` for a bank given as channels -> sections -> (b, a)."""
+def device_bank(bank_sections, parallel=False):
+  """Cached :class:`DeviceBank` for a bank given as channels -> sections -> (b, a). ``parallel``: the bank is the
+  member list of a ParallelFilter (plain float64 sections, summed inside one kernel)."""
   torch = torch_mod()
-  key = (torch.cuda.current_device(), _key(bank_sections))
+  key = (torch.cuda.current_device(), bool(parallel), _key(bank_sections))
   with _lock:
     db = _cache.get(key)
     if db is None:
       if len(_cache) > 256:
         _cache.clear()
-      db = _cache[key] = DeviceBank(bank_sections)
+      db = _cache[key] = DeviceBank(bank_sections, parallel=parallel)
   return db
+
+
+def _to_f32(chunk):
+  """list / tuple of Python numbers -> float32 ndarray. ``array('d', ...)`` walks the objects in C about twice as
+  fast as ``np.asarray`` does; anything it refuses (complex, nested, None) goes the numpy way and raises there."""
+  try:
+    return np.frombuffer(array("d", chunk), dtype=np.float64).astype(np.float32)
+  except (TypeError, OverflowError):
+    return np.asarray(chunk, dtype=np.float32)
 
 
 def _blocks(seq):
@@ -133,7 +168,7 @@ def _blocks(seq):
     return
   if isinstance(seq, (list, tuple)):
     for i in range(0, len(seq), MAX_BLOCK):
-      yield np.asarray(seq[i:i + MAX_BLOCK], dtype=np.float32)
+      yield _to_f32(seq if len(seq) <= MAX_BLOCK else seq[i:i + MAX_BLOCK])
     return
   src = iter(seq)
   n = FIRST_BLOCK
@@ -141,7 +176,42 @@ def _blocks(seq):
     chunk = list(it.islice(src, n))
     if not chunk:
       return
-    yield np.asarray(chunk, dtype=np.float32)
+    yield _to_f32(chunk)
+    if len(chunk) < n:
+      return
+    n = min(n * 4, MAX_BLOCK)
+
+
+class _Blocks(object):
+  """Marker: an iterable of ready float32 blocks (see :func:`_pre_blocks`)."""
+
+  def __init__(self, gen):
+    self.gen = gen
+
+
+def _pre_blocks(seq, pre):
+  def gen():
+    for xb in _blocks64(seq):
+      yield pre(xb).astype(np.float32)
+  return _Blocks(gen())
+
+
+def _blocks64(seq):
+  """As :func:`_blocks` but float64 blocks (the pre-op runs on the values the reference's Stream arithmetic sees)."""
+  if isinstance(seq, np.ndarray) and seq.ndim == 1:
+    for i in range(0, len(seq), MAX_BLOCK):
+      yield np.asarray(seq[i:i + MAX_BLOCK], dtype=np.float64)
+    return
+  src = iter(seq)
+  n = FIRST_BLOCK if not isinstance(seq, (list, tuple)) else MAX_BLOCK
+  while True:
+    chunk = list(it.islice(src, n))
+    if not chunk:
+      return
+    try:
+      yield np.frombuffer(array("d", chunk), dtype=np.float64)
+    except (TypeError, OverflowError):
+      yield np.asarray(chunk, dtype=np.float64)
     if len(chunk) < n:
       return
     n = min(n * 4, MAX_BLOCK)
@@ -151,24 +221,28 @@ def _pump(db, seq, xinit, yinit, sum_channels):
   """Generator of per-block results: numpy float32 ``[C, n]`` (or ``[n]`` when summed)."""
   torch = torch_mod()
   state = None
-  for xb in _blocks(seq):
+  for xb in (seq.gen if isinstance(seq, _Blocks) else _blocks(seq)):
     if state is None:
       state = db.new_state(1, xinit, yinit)
     x_dev = torch.from_numpy(xb).to(db.device, non_blocking=False)
-    y_dev = db.apply(x_dev, state)
     if sum_channels:
-      yield db.sum_channels(y_dev)[0].cpu().numpy()
+      yield db.apply_sum(x_dev, state)[0].cpu().numpy()
     else:
-      yield y_dev[0].cpu().numpy()
+      yield db.apply(x_dev, state)[0].cpu().numpy()
 
 
-def filter_stream(bank_sections, seq, xinit, yinit, sum_channels=False):
-  """Lazy Stream of a single-output filter call (one channel, or the channel sum)."""
-  db = device_bank(bank_sections)   # errors (zero gain, no device) raise at call time, like the reference
+def filter_stream(bank_sections, seq, xinit, yinit, sum_channels=False, pre=None, post=None):
+  """Lazy Stream of a single-output filter call (one channel, or the channel sum). ``pre`` / ``post``: numpy
+  ufunc-like callables applied to each input block (float64, before the float32 conversion) / output block
+  (float64) -- the x**2, abs, sqrt around the lowpass of ``envelope.*`` without a Python frame per sample."""
+  db = device_bank(bank_sections, parallel=sum_channels)   # errors (zero gain, no device) raise at call time, like the reference
+  if pre is not None:
+    seq = _pre_blocks(seq, pre)
 
   def rows():
     for block in _pump(db, seq, xinit, yinit, sum_channels):
-      yield (block if sum_channels else block[0]).tolist()
+      row = block if sum_channels else block[0]
+      yield (row if post is None else post(row.astype(np.float64))).tolist()
 
   # chain.from_iterable walks the per-block lists in C: no Python frame per sample
   return Stream(it.chain.from_iterable(rows()))

@@ -62,22 +62,39 @@ def white_noise(dur=None, low=-1., high=1.):
 envelope = StrategyDict("envelope")
 
 
+def _envelope(sig, cutoff, pre, post):
+  """``post(lowpass(cutoff)(pre(sig)))`` (reference ``lazy_analysis.py:440-520``). With a constant cutoff the
+  rectifier / squarer and the square root run on whole blocks next to the device launch (numpy, float64, the values
+  the reference's Stream arithmetic produces) instead of one Python frame per sample; a Stream-valued cutoff keeps
+  the elementwise Stream expression around the time-varying filter."""
+  import numpy as np
+  from . import _engine
+  from .filters import _seed_histories
+  filt = lowpass(cutoff)
+  ops = {"square": (np.square, lambda s: s ** 2), "abs": (np.abs, abs), "sqrt": (np.sqrt, lambda s: s ** .5), None: (None, lambda s: s)}
+  if filt.is_lti():
+    secs = filt.sections()
+    xinit, yinit = _seed_histories(secs, None, 0.)
+    return _engine.filter_stream([secs], sig, [xinit], [yinit], pre=ops[pre][0], post=ops[post][0])
+  return ops[post][1](filt(ops[pre][1](thub(sig, 1))))
+
+
 @envelope.strategy("rms")
 def envelope(sig, cutoff=pi / 512):
   """RMS envelope: lowpass of the squared signal, then square root."""
-  return lowpass(cutoff)(thub(sig, 1) ** 2) ** .5
+  return _envelope(sig, cutoff, "square", "sqrt")
 
 
 @envelope.strategy("abs")
 def envelope(sig, cutoff=pi / 512):
   """Lowpass of the rectified signal."""
-  return lowpass(cutoff)(abs(thub(sig, 1)))
+  return _envelope(sig, cutoff, "abs", None)
 
 
 @envelope.strategy("squared")
 def envelope(sig, cutoff=pi / 512):
   """Lowpass of the squared signal."""
-  return lowpass(cutoff)(thub(sig, 1) ** 2)
+  return _envelope(sig, cutoff, "square", None)
 
 
 # ---- moving average ----------------------------------------------------------------------

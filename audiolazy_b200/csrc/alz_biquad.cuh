@@ -179,7 +179,10 @@ struct AlzBiquadCore {
   }
 
   // Steady state: section k reads the history of section k-1's output.
-  __host__ __device__ __forceinline__ float step_alias(W xin) {
+  __host__ __device__ __forceinline__ float step_alias(W xin) { return (float)step_alias_w(xin); }
+  __host__ __device__ __forceinline__ float step_explicit(W xin) { return (float)step_explicit_w(xin); }
+
+  __host__ __device__ __forceinline__ W step_alias_w(W xin) {
     W in = xin, in1, in2;
     if (NB0 > 3) {
       in1 = u[1][0]; in2 = u[1][1];       // section 1 reads section 0's OLD output history
@@ -197,11 +200,11 @@ struct AlzBiquadCore {
       u[k + 1][0] = y;
       in = y; in1 = y1; in2 = y2;
     }
-    return (float)(MONIC == 1 ? G * in : in);
+    return MONIC == 1 ? G * in : in;
   }
 
   // First two samples of a launch: explicit input histories.
-  __host__ __device__ __forceinline__ float step_explicit(W xin) {
+  __host__ __device__ __forceinline__ W step_explicit_w(W xin) {
     W in = xin;
     if (NB0 > 3) in = head(xin);
 #pragma unroll
@@ -215,7 +218,7 @@ struct AlzBiquadCore {
       u[k + 1][0] = y;
       in = y;
     }
-    return (float)(MONIC == 1 ? G * in : in);
+    return MONIC == 1 ? G * in : in;
   }
 
   // float32 sample -> float64 section input (with the input-side gain when MONIC == 2)
@@ -264,6 +267,21 @@ struct AlzBiquadCore {
         const W xin = widen(*p);
         *p = (n_done + j < 2) ? step_explicit(xin) : step_alias(xin);
       }
+    }
+  }
+
+  // ParallelFilter (alz_parallel.cuh): this channel's UNROUNDED outputs of one tile are added to acc[] (registers,
+  // left-associated over the channels as reference lazy_filters.py:1053-1054); the input row is left untouched.
+  // Always called right after load(): the first two samples use the explicit histories.
+  template <int J>
+  __device__ __forceinline__ void acc_from(const float* xrow, int swz, int nvalid, bool first, W (&acc)[ALZ_TT]) {
+    if constexpr (J < ALZ_TT) {
+      if (J < nvalid) {
+        const W xin = widen(xrow[(((J >> 2) ^ swz) << 2) | (J & 3)]);
+        const W y = J < 2 ? step_explicit_w(xin) : step_alias_w(xin);
+        acc[J] = first ? y : acc[J] + y;
+      }
+      acc_from<J + 1>(xrow, swz, nvalid, first, acc);
     }
   }
 

@@ -144,6 +144,18 @@ bool alzi_make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap*
   return true;
 }
 
+// rows[n_rows][T] float32 (row stride `stride` elements) with 32 x 32 boxes
+static bool make_map_2d(const float* ptr, long long T, long long n_rows, long long stride, CUtensorMap* tm) {
+  alz_encode_tiled_fn enc = get_encode_tiled();
+  if (!enc || ((uintptr_t)ptr & 15) || (stride & 3) || T >= (1ll << 31) || n_rows >= (1ll << 31)) return false;
+  const cuuint32_t estr[2] = {1, 1};
+  const cuuint64_t dims[2] = {(cuuint64_t)T, (cuuint64_t)n_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride * 4};
+  const cuuint32_t box[2] = {32, 32};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int launch_biquad(const alz_plan* p, const AlzTileArgs& ta, cudaStream_t st) {
   if (p->NB0 == 8) {
     if (p->K == 1) return alzi_launch_headfir_k1(p, ta, st);
@@ -261,6 +273,7 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
   p->C = C;
   p->device = dev;
   p->sequential = (flags & ALZ_PLAN_SEQUENTIAL) != 0;
+  p->parallel_sum = (flags & ALZ_PLAN_PARALLEL) != 0;
   if (design_only || cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || p->sm_count <= 0) {
     cudaGetLastError();
     p->sm_count = 148;
@@ -297,7 +310,7 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
     p->xd = ALZ_H0(p->NB0); p->yd = 2;
     p->state_doubles = ALZ_STATE_SLOTS(K, p->NB0);
     // monic only if every b0 is a normal number and the running products stay normal
-    bool monic = true;
+    bool monic = !p->parallel_sum;          // ParallelFilter plans keep plain sections: the channel outputs are summed in true units
     for (int c = 0; c < C && monic; ++c) {
       double g = 1.0;
       for (auto& s : secs[c]) {
@@ -373,7 +386,7 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
     p->tier_err.assign(C, -1.0);
     p->tier_tol = env_double("ALZ_TIER_TOL", 2.5e-6);
     p->probe_len = std::max(64, env_int("ALZ_TIER_PROBE", 8192));
-    const bool tiering = !(flags & ALZ_PLAN_EXACT) && !env_int("ALZ_NO_FP32_TIER", 0) && p->tier_tol > 0.0;
+    const bool tiering = !(flags & ALZ_PLAN_EXACT) && !p->parallel_sum && !env_int("ALZ_NO_FP32_TIER", 0) && p->tier_tol > 0.0;
     std::vector<double> tab32((size_t)C * stride, 0.0);   // the same records as packed floats
     for (int c = 0; c < C; ++c) {
       const double* rec = tab.data() + (size_t)c * stride;
@@ -806,20 +819,21 @@ static bool chunk_geometry(const alz_plan* p, const float* x, const float* y, lo
   // channel-sample); the machine as a whole does ~1.2e12 channel-samples/s and the chunked evaluation runs 2 passes + extras
   const double work = std::max(1, p->fp64_ops) / 12.0;
   const double t_seq = (double)T * 36e-9 * work;
-  const double t_par = 2.6 * (double)S * (double)T * p->C * work / 1.2e12 + 1e-4;
-  if (t_par > 0.8 * t_seq) return false;
-  long long Pmax = (2 * slots * 32 + p->C * S - 1) / (p->C * S);   // virtual warps ~ 2 x resident slots
-  Pmax = (Pmax + 31) / 32 * 32;
-  if (Pmax > 1024) Pmax = 1024;                    // the scan over the chunks of a stream is serial (~200 cycles per chunk)
-  if (Pmax * 256 > T) Pmax = T / 256 / 32 * 32;    // chunks of at least 256 samples
-  if (Pmax < 32) return false;
-  // chunks are whole tiles (L % 32 == 0), so T mod 32 P samples are left over for a sequential tail: among the chunk
-  // counts near the target take the one with the shortest tail
-  long long P = Pmax, best_tail = T % (32 * Pmax);
-  for (long long q = Pmax - 32; q >= 32 && q * 2 >= Pmax; q -= 32) {
-    const long long tail = T % (32 * q);
-    if (tail < best_tail) { best_tail = tail; P = q; }
+  // Chunk count P (a multiple of 32, chunks of >= 256 samples, <= 1024 because the scan over a stream's chunks is
+  // serial): the one with the smallest estimated time.  A pass over all chunks costs ceil(waves) x L samples at the
+  // per-sample time of a warp on a machine `occ` full (36 ns alone ... 92 ns with all 24 warp slots of its SM busy);
+  // chunks are whole tiles, so T mod 32 P samples are left over for a sequential tail.
+  long long P = 0;
+  double best = 1e30;
+  for (long long q = 32; q <= 1024 && q * 256 <= T; q += 32) {
+    const double waves = (double)p->C * S * q / 32.0 / (double)slots;
+    const double occ = waves < 1.0 ? waves : 1.0;
+    const long long Lq = T / q / 32 * 32, tail = T - q * Lq;
+    const double t_sample = std::max(36e-9, 92e-9 * occ) * work;
+    const double t = 2.0 * std::ceil(waves) * (double)Lq * t_sample + (double)tail * 36e-9 * work + (double)q * 1e-7;
+    if (t < best) { best = t; P = q; }
   }
+  if (P == 0 || best + 5e-5 > 0.8 * t_seq) return false;
   const long long L = T / P / 32 * 32;
   if (L < 256) return false;
   *P_out = P;
@@ -949,6 +963,32 @@ int32_t alz_apply_f32_ex(const alz_plan* p, const float* x, float* y, double* st
   ALZ_CUDA(cudaGetDevice(&cur));
   if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
   const int rc = apply_impl(p, x, y, state, (long long)S * p->C, S, T, xs, ys, (cudaStream_t)cuda_stream, nullptr, 0, y_stream_stride);
+  if (cur != p->device) cudaSetDevice(cur);
+  return rc;
+}
+
+int32_t alz_apply_sum_f32(const alz_plan* p, const float* x, float* out, double* state, int64_t S, int64_t T,
+                          int64_t xs, int64_t os, void* cuda_stream) {
+  if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (p->device < 0) return fail(ALZ_ERR_CUDA, "design-only plan: no device");
+  if (S < 0 || T < 0) return fail(ALZ_ERR_INVALID, "negative size");
+  if (S == 0 || T == 0) return ALZ_OK;
+  if (!x || !out || !state) return fail(ALZ_ERR_INVALID, "null buffer");
+  if (xs < T || os < T) return fail(ALZ_ERR_INVALID, "row stride shorter than n_samples");
+  if (p->kind != ALZ_KIND_BIQUAD || !p->parallel_sum || p->NB0 != 0 || p->monic != 0 || p->chunks.size() != 1)
+    return fail(ALZ_ERR_UNSUPPORTED, "alz_apply_sum_f32 needs a biquad plan created with ALZ_PLAN_PARALLEL");
+  if (S > 65535ll * 32) return fail(ALZ_ERR_UNSUPPORTED, "too many streams for one launch");
+  CUtensorMap tmx, tmo;
+  if (env_int("ALZ_NO_TMA", 0) || !make_map_2d(x, T, S, xs, &tmx) || !make_map_2d(out, T, S, os, &tmo))
+    return fail(ALZ_ERR_UNSUPPORTED, "alz_apply_sum_f32 needs 16-byte aligned rows (use alz_apply_f32 + alz_sum_channels_f32)");
+  int cur = -1;
+  ALZ_CUDA(cudaGetDevice(&cur));
+  if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
+  AlzTileArgs ta{};
+  ta.x = x; ta.y = out; ta.S = S; ta.T = T; ta.xs = xs; ta.ys = os; ta.ysS = os; ta.C = p->C; ta.Stot = S;
+  ta.state = state; ta.sstride = (long long)S * p->C;
+  ta.vec_in = ta.vec_out = 1;
+  const int rc = alzi_launch_parallel(p, ta, tmx, tmo, (cudaStream_t)cuda_stream);
   if (cur != p->device) cudaSetDevice(cur);
   return rc;
 }

@@ -2,6 +2,7 @@
 // translation units (alz_capi.cu = the C ABI; alz_inst_*.cu = the biquad kernel instantiations,
 // split by cascade length so that they compile in parallel).  Nothing here is exported.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdarg>
@@ -53,6 +54,7 @@ struct alz_plan {
   double tier_tol = 0.0;       // measured-error threshold the tier decision used
   int probe_len = 8192;        // samples per probe signal of the tier decision
   int tile_group = 2;          // TMA engine: tiles moved together by launches that fill the machine (1, 2, 4)
+  bool parallel_sum = false;   // ALZ_PLAN_PARALLEL: plain float64 records, usable by alz_apply_sum_f32
   bool sequential = false;     // ALZ_PLAN_SEQUENTIAL: never evaluate time-parallel (bit-reproducible blocking)
   bool coef_small = false;     // kernel-parameter block size (kCoefSmall / kCoefLarge doubles)
   struct Chunk { void* block; int npos; };
@@ -104,6 +106,7 @@ int alzi_launch_headfir_k1(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 int alzi_launch_headfir_k4(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 
 int alzi_launch_window(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_parallel(const alz_plan*, const AlzTileArgs&, const CUtensorMap& tmx, const CUtensorMap& tmo, cudaStream_t);
 size_t alzi_window_block_bytes(bool small);
 void alzi_window_block_fill(void* blk, bool small, int n_far_x, int n_far_y, int xbase, int xmask, int ybase, int ymask, int xwin,
                             int ywin, int C, const int* far_delay, const double* far_coef, const double* coef);
@@ -121,5 +124,4 @@ double alzi_probe_headfir_k1(const alz_plan*, const double* rec64, const double*
 double alzi_probe_headfir_k4(const alz_plan*, const double* rec64, const double* rec32);
 
 // tensor maps of x[S][T] / y[S][C][T] (alz_capi.cu)
-#include <cuda.h>
 bool alzi_make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap* tmy);

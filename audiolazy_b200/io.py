@@ -42,9 +42,10 @@ def chunks(seq, size=None, dfmt="f", byte_order=None, padval=0.):
     yield packer.pack(*block)
 
 
-def pcm_to_float32(raw, bits, keep=False):
-  """Decode little-endian PCM bytes to samples: float32 in ``[-1, 1)`` (``value / 2**(bits-1)``;
-  8-bit data is unsigned, offset 128), or the stored integers when ``keep``."""
+def pcm_to_float32(raw, bits, keep=False, dtype=np.float32):
+  """Decode little-endian PCM bytes to samples in ``[-1, 1)`` (``value / 2**(bits-1)``; 8-bit data is unsigned,
+  offset 128), or the stored integers when ``keep``. ``dtype=np.float32`` (default) is what the device path
+  consumes; ``np.float64`` is exact for every width, as the reference's ``int / int`` (``lazy_wav.py:117-123``)."""
   if bits == 8:
     data = np.frombuffer(raw, dtype=np.uint8).astype(np.int32) - (0 if keep else 128)
   elif bits == 16:
@@ -59,7 +60,7 @@ def pcm_to_float32(raw, bits, keep=False):
     raise ValueError("unsupported sample width: %d bits" % bits)
   if keep:
     return data
-  return (data / float(1 << (bits - 1))).astype(np.float32)
+  return (data / float(1 << (bits - 1))).astype(dtype)
 
 
 class WavStream(Stream):
@@ -80,8 +81,8 @@ class WavStream(Stream):
           raw = w.readframes(4096)
           if not raw:
             break
-          block = pcm_to_float32(raw, self.bits, keep=keep)
-          for value in (block.tolist() if keep else block.astype(np.float64).tolist()):
+          # float64: 24- and 32-bit samples do not fit a float32 mantissa, the reference yields int / 2**(bits-1) exactly
+          for value in pcm_to_float32(raw, self.bits, keep=keep, dtype=np.float64).tolist():
             yield value
       finally:
         w.close()

@@ -122,6 +122,9 @@ int32_t alz_plan_create(const double* coef, const int32_t* section_desc,
 /* ALZ_PLAN_SEQUENTIAL: never use the time-parallel evaluation (see alz_apply_f32): every call is
  * evaluated sample by sample, so ANY blocking of a stream gives the same bits. */
 #define ALZ_PLAN_SEQUENTIAL 8
+/* ALZ_PLAN_PARALLEL: the plan is the member list of a ParallelFilter (reference lazy_filters.py:1024-1084):
+ * plain float64 sections, every channel on the float64 tier; alz_apply_sum_f32 evaluates the sum in one kernel. */
+#define ALZ_PLAN_PARALLEL 16
 int32_t alz_plan_create_ex(const double* coef, const int32_t* section_desc, int32_t n_channels,
                            int32_t max_sections, int32_t flags, alz_plan** out);
 
@@ -225,6 +228,18 @@ int32_t alz_apply_f32_host(const alz_plan* plan, const float* x_host, float* y_h
  */
 int32_t alz_host_alloc(void** out, int64_t bytes, int32_t device, int32_t* numa_node);
 int32_t alz_host_free(void* ptr);
+
+/*
+ * ParallelFilter.__call__ in ONE kernel (reference lazy_filters.py:1048-1054): out[s][t] =
+ * ((y_0[s][t] + y_1[s][t]) + ...) over the plan's channels, summed left to right in float64 over the
+ * float64 channel results, rounded to float32 once.  The channel outputs never reach memory: 8 bytes
+ * of HBM traffic per input sample.  Needs a biquad plan created with ALZ_PLAN_PARALLEL and 16-byte
+ * aligned x / out rows (else ALZ_ERR_UNSUPPORTED: use alz_apply_f32 + alz_sum_channels_f32).
+ * x_dev [n_streams][n_samples], out_dev [n_streams][n_samples]; state as alz_apply_f32.
+ */
+int32_t alz_apply_sum_f32(const alz_plan* plan, const float* x_dev, float* out_dev, double* state_dev,
+                          int64_t n_streams, int64_t n_samples, int64_t x_stride, int64_t out_stride,
+                          void* cuda_stream);
 
 /*
  * ParallelFilter reduction: out[s][t] = ((y[s][0][t] + y[s][1][t]) + ...) over

@@ -26,7 +26,7 @@ class FakePlan(object):
   """Same surface as ``_capi.Plan`` for what the engine uses."""
   states = {}      # state pointer -> dict
 
-  def __init__(self, bank, force_generic=False):
+  def __init__(self, bank, force_generic=False, parallel=False, **_flags):
     self.bank = [[([float(v) for v in b] or [0.0], [float(v) for v in a]) for b, a in ch] for ch in bank]
     for ch in self.bank:
       for b, a in ch:
@@ -38,6 +38,7 @@ class FakePlan(object):
     self.xd = max([len(b) - 1 for ch in self.bank for b, _ in ch] + [0])
     self.yd = max([len(a) - 1 for ch in self.bank for _, a in ch] + [0])
     self.kind = 2 if force_generic else 1
+    self.num_taps = max([len(b) for ch in self.bank for b, _ in ch] + [1])
     self.launches = 0
 
   # ---- state: the whole input history is kept and the oracle re-runs from the start (tests are small)
@@ -62,6 +63,22 @@ class FakePlan(object):
       for c in range(C):
         off = (s * C + c) * y_stride
         y[off:off + T] = full[s, c, -T:].astype(np.float32)
+    self.launches += 1
+
+  def apply_sum(self, x_ptr, out_ptr, state_ptr, n_streams, n_samples, x_stride, out_stride, stream=0):
+    """ParallelFilter in one call: float64 channel results summed left to right, rounded to float32 once."""
+    S, T = int(n_streams), int(n_samples)
+    st = FakePlan.states[int(state_ptr)]
+    x = _f32(x_ptr, (S - 1) * x_stride + T).copy() if S > 1 else _f32(x_ptr, T).copy()
+    rows = np.stack([x[s * x_stride:s * x_stride + T] for s in range(S)])
+    st["x"] = np.concatenate([st["x"], rows], axis=1)
+    full = oracle.bank_apply(st["x"], self._padded_bank(), xinit=st["xi"], yinit=st["yi"])
+    out = _f32(out_ptr, (S - 1) * out_stride + T)
+    for s in range(S):
+      acc = full[s, 0, -T:].copy()
+      for c in range(1, self.n_channels):
+        acc = acc + full[s, c, -T:]
+      out[s * out_stride:s * out_stride + T] = acc.astype(np.float32)
     self.launches += 1
 
   def _padded_bank(self):

@@ -46,6 +46,17 @@ def test_wavstream_matches_reference(reference):
   assert list(ab.WavStream(make_wav(16, 1, values))) == pytest.approx(want, rel=1e-7, abs=1e-9)
 
 
+@pytest.mark.parametrize("bits", [8, 16, 24, 32])
+def test_wavstream_matches_reference_every_width(reference, bits):
+  """Byte formats must be bit-exact: same floats (and same ints with keep=True) as the reference's WavStream."""
+  top = 1 << (bits - 1)
+  values = [0, 1, -1, top - 1, -top, top // 3, -(top // 7), 12345 % top, -(54321 % top)]
+  for channels in (1, 2):
+    vals = values if channels == 1 else values + values[::-1]
+    assert list(ab.WavStream(make_wav(bits, channels, vals))) == list(reference.WavStream(make_wav(bits, channels, vals)))
+    assert list(ab.WavStream(make_wav(bits, channels, vals), keep=True)) == list(reference.WavStream(make_wav(bits, channels, vals), keep=True))
+
+
 def test_chunks():
   blocks = list(ab.chunks([.1, .2, .3, .4, .5], size=2))
   assert len(blocks) == 3 and all(len(b) == 8 for b in blocks)

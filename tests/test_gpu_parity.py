@@ -393,3 +393,75 @@ def test_experimental_wide_cta_engine(gpu, designs, monkeypatch):
       assert torch.equal(outs[0][0][:, :, :T], outs[1][0][:, :, :T]), (name, S, T)
       assert bool(torch.isnan(outs[1][0][:, :, T:]).all()), (name, S, T)
       assert torch.equal(outs[0][1], outs[1][1]), (name, S, T)
+
+
+def test_parallel_sum_in_one_kernel(gpu, designs):
+  """alz_apply_sum_f32 (ParallelFilter, reference lazy_filters.py:1048-1054): float64 channel results summed left to
+  right inside ONE kernel, one rounding to float32; against the oracle's float64 channel outputs summed the same way."""
+  torch = gpu.torch
+  for bank in (designs["bank_slaney"][:8], designs["bank_klapuri"][40:43], [[([1.0, 0.5], [1.0, -0.9])], [([-1.0, -0.5], [1.0, -0.9001])]]):
+    plan = gpu.capi.Plan(bank, parallel=True)
+    assert plan.kind == gpu.capi.KIND_BIQUAD and plan.n_fp32_channels == 0 and not plan.monic
+    S, T = 70, 5000
+    x = np.random.default_rng(len(bank)).uniform(-1, 1, (S, T)).astype(np.float32)
+    ch = oracle.bank_apply(x, bank)
+    want = ch[:, 0].copy()
+    for c in range(1, len(bank)):
+      want = want + ch[:, c]
+    xd = torch.from_numpy(x).to(gpu.dev)
+    out = torch.full((S, T), float("nan"), dtype=torch.float32, device=gpu.dev)
+    st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=gpu.dev)
+    cur = torch.cuda.current_stream().cuda_stream
+    before = gpu.capi.launch_count()
+    plan.apply_sum(xd.data_ptr(), out.data_ptr(), st.data_ptr(), S, T, T, T, cur)
+    torch.cuda.synchronize()
+    assert gpu.capi.launch_count() - before == 1
+    got = out.cpu().numpy()
+    assert rel_err(got, want) <= 2.5e-7          # relative to the SUMMED signal's peak, also under heavy cancellation (third bank)
+    # blocks: the state buffer carries every channel between calls, bit for bit
+    out2 = torch.empty_like(out)
+    st.zero_()
+    for t0, n in ((0, 1), (1, 37), (38, 2010), (2048, T - 2048)):
+      plan.apply_sum(xd.data_ptr() + 4 * t0, out2.data_ptr() + 4 * t0, st.data_ptr(), S, n, T, T, cur)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+  # unaligned rows are refused loudly (the caller then uses alz_apply_f32 + alz_sum_channels_f32)
+  with pytest.raises(gpu.capi.NativeError):
+    plan.apply_sum(xd.data_ptr() + 4, out.data_ptr(), st.data_ptr(), S, T - 1, T, T, cur)
+
+
+@pytest.mark.parametrize("bits", [8, 16, 24, 32])
+def test_wav_to_bank_to_chunks(gpu, designs, tmp_path, bits):
+  """the formats either side of the path -- PCM wave files in (reference lazy_wav.py:31-130), float32
+  chunks out (lazy_io.py:48-128) -- around the device bank.  Decoding and packing are exact; the filtering is within the bar."""
+  import struct
+  import wave
+  import audiolazy_b200 as ab
+  top = 1 << (bits - 1)
+  rng = np.random.default_rng(bits)
+  paths, ints = [], []
+  for i in range(3):
+    v = rng.integers(-top, top, 3000 + 100 * i).tolist()
+    ints.append(v)
+    path = str(tmp_path / ("s%d.wav" % i))
+    with wave.open(path, "wb") as w:
+      w.setnchannels(1); w.setsampwidth(bits // 8); w.setframerate(48000)
+      if bits == 8:
+        w.writeframes(bytes((q + 128) & 0xff for q in v))
+      elif bits == 24:
+        w.writeframes(b"".join(struct.pack("<i", q)[:3] for q in v))
+      else:
+        w.writeframes(struct.pack("<%d%s" % (len(v), "h" if bits == 16 else "i"), *v))
+    paths.append(path)
+  batch, lengths, rates = ab.wav_batch(paths)
+  assert lengths == [len(v) for v in ints] and rates == [48000] * 3
+  for i, v in enumerate(ints):                        # exact: float32(int / 2**(bits-1)), zero padded
+    assert np.array_equal(batch[i, :len(v)], (np.asarray(v, dtype=np.float64) / top).astype(np.float32))
+    assert not batch[i, len(v):].any()
+    assert list(ab.WavStream(paths[i])) == [q / top for q in v]          # the lazy reader: the reference's exact float64
+  bank = ab.FilterBank([ab.gammatone.slaney(f * ab.sHz(48000)[1], 0.02) for f in (300., 1200., 5000.)])
+  y = bank.apply(gpu.torch.from_numpy(batch).to(gpu.dev)).cpu().numpy()
+  assert rel_err(y, oracle.bank_apply(batch, bank.sections())) <= TOL
+  row = y[1, 2, :lengths[1]]
+  blocks = list(ab.chunks(row.tolist(), size=1024))
+  assert b"".join(blocks) == np.concatenate([row, np.zeros(-len(row) % 1024, dtype=np.float32)]).astype("<f4").tobytes()
