@@ -830,10 +830,13 @@ static bool chunk_geometry(const alz_plan* p, const float* x, const float* y, lo
     const double occ = waves < 1.0 ? waves : 1.0;
     const long long Lq = T / q / 32 * 32, tail = T - q * Lq;
     const double t_sample = std::max(36e-9, 92e-9 * occ) * work;
-    const double t = 2.0 * std::ceil(waves) * (double)Lq * t_sample + (double)tail * 36e-9 * work + (double)q * 1e-7;
+    // + the chunk states: d doubles per (channel, virtual stream), written / scanned / read ~6 times at ~4 TB/s;
+    // + ~10 us per wave and pass of CTA start-up and wave-end imbalance; + the serial scan, ~0.1 us per chunk
+    const double t_state = 6.0 * p->state_doubles * 8.0 * p->C * (double)S * (double)q / 4e12;
+    const double t = 2.0 * std::ceil(waves) * ((double)Lq * t_sample + 1e-5) + t_state + (double)tail * 36e-9 * work + (double)q * 1e-7;
     if (t < best) { best = t; P = q; }
   }
-  if (P == 0 || best + 5e-5 > 0.8 * t_seq) return false;
+  if (P == 0 || 1.25 * best + 5e-5 > 0.8 * t_seq) return false;   // the estimate is ~20 % optimistic (measured)
   const long long L = T / P / 32 * 32;
   if (L < 256) return false;
   *P_out = P;

@@ -421,7 +421,7 @@ def test_parallel_sum_in_one_kernel(gpu, designs):
     # blocks: the state buffer carries every channel between calls, bit for bit
     out2 = torch.empty_like(out)
     st.zero_()
-    for t0, n in ((0, 1), (1, 37), (38, 2010), (2048, T - 2048)):
+    for t0, n in ((0, 4), (4, 36), (40, 2008), (2048, T - 2048)):        # 16-byte aligned block starts (TMA rows)
       plan.apply_sum(xd.data_ptr() + 4 * t0, out2.data_ptr() + 4 * t0, st.data_ptr(), S, n, T, T, cur)
     torch.cuda.synchronize()
     assert torch.equal(out, out2)
