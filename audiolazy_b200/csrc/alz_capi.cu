@@ -126,18 +126,19 @@ bool alzi_make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap*
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)ta.T, (cuuint64_t)ta.S};
-    const cuuint64_t strides[1] = {(cuuint64_t)ta.xs * 4};
-    const cuuint32_t box[2] = {32, 32};
-    if (enc(tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ta.x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    // real streams, same ranks as the virtual case so that the kernels have ONE code path: x (T, S, 1), y (T, C, S, 1)
+    const cuuint64_t dims[3] = {(cuuint64_t)ta.T, (cuuint64_t)ta.S, 1};
+    const cuuint64_t strides[2] = {(cuuint64_t)ta.xs * 4, (cuuint64_t)ta.xs * 4};
+    const cuuint32_t box[3] = {32, 32, 1};
+    if (enc(tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ta.x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return false;
   }
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)ta.T, (cuuint64_t)ta.C, (cuuint64_t)ta.S};
-    const cuuint64_t strides[2] = {(cuuint64_t)ta.ys * 4, (cuuint64_t)ta.ysS * 4};
-    const cuuint32_t box[3] = {32, 1, 32};
-    if (enc(tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ta.y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t dims[4] = {(cuuint64_t)ta.T, (cuuint64_t)ta.C, (cuuint64_t)ta.S, 1};
+    const cuuint64_t strides[3] = {(cuuint64_t)ta.ys * 4, (cuuint64_t)ta.ysS * 4, (cuuint64_t)ta.ysS * 4};
+    const cuuint32_t box[4] = {32, 1, 32, 1};
+    if (enc(tmy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)ta.y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
       return false;
   }
@@ -404,7 +405,8 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
     // ---- positions: interleave the tiers along blockIdx.x so both kinds of warp share every SM ----
     {
       std::vector<int> lst[2];
-      for (int c = 0; c < C; ++c) lst[p->tier[c]].push_back(c);
+      const int order = env_int("ALZ_TIER_ORDER", 1);   // 1: interleave the tiers; 0: channel order; 2: float32 channels first
+      for (int c = 0; c < C; ++c) lst[order == 1 ? p->tier[c] : (order == 2 ? 1 - p->tier[c] : 0)].push_back(c);
       size_t i0 = 0, i1 = 0;
       p->pos_channel.clear();
       while (i0 < lst[0].size() || i1 < lst[1].size()) {   // Bresenham merge: the list that is less consumed goes next

@@ -60,15 +60,6 @@ __device__ __forceinline__ void alz_tma_store_4d(const CUtensorMap* map, int c0,
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n"
                ::"l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src) : "memory");
 }
-// tile load / store of stream group s0 (virtual streams: chunk p0 = s0 % vP of real stream s0 / vP)
-__device__ __forceinline__ void alz_tile_load(const AlzTileArgs& a, unsigned dst, const CUtensorMap* tmx, int t, long long s0, unsigned mbar) {
-  if (a.vP > 0) alz_tma_load_3d(dst, tmx, t, (int)(s0 % a.vP), (int)(s0 / a.vP), mbar);
-  else alz_tma_load_2d(dst, tmx, t, (int)s0, mbar);
-}
-__device__ __forceinline__ void alz_tile_store(const AlzTileArgs& a, const CUtensorMap* tmy, int t, int c, long long s0, unsigned src) {
-  if (a.vP > 0) alz_tma_store_4d(tmy, t, (int)(s0 % a.vP), c, (int)(s0 / a.vP), src);
-  else alz_tma_store_3d(tmy, t, c, (int)s0, src);
-}
 __device__ __forceinline__ void alz_bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void alz_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void alz_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
@@ -105,6 +96,15 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   const long long s = s0 + lane;
   const bool valid = s < a.S;
   const long long r = (long long)c * a.Stot + (valid ? s : a.S - 1);   // stream-fastest: coalesced state access
+  // TMA coordinates of this stream group, computed once (ONE code path in the tile loop: x is always a 3-D map, y a 4-D
+  // map).  Real streams: x (t, stream, 0), y (t, channel, stream, 0).  Virtual streams (time-parallel evaluation): row v
+  // is chunk v % vP of real stream v / vP: x (t, chunk, stream), y (t, chunk, channel, stream).
+  int ld1 = (int)s0, ld2 = 0, st1 = c, st2 = (int)s0, st3 = 0;
+  if (a.vP > 0) {
+    ld2 = (int)(s0 / a.vP);
+    ld1 = (int)(s0 - (long long)ld2 * a.vP);
+    st1 = ld1; st2 = c; st3 = ld2;
+  }
 
   const int NG = a.paired < 2 ? 1 : a.paired;   // tiles per group (1 = one tile at a time with a prefetch)
   const int nbuf = NG < 2 ? 2 : NG;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   const int lg = NG >= 4 ? 2 : (NG >= 2 ? 1 : 0);
   if (lane == 0 && NG == 1) {   // tile 0 in flight
     alz_mbar_expect_tx(mbar0, ALZ_TMA_TILE_BYTES);
-    alz_tile_load(a, tile0, tmx, tb, s0, mbar0);
+    alz_tma_load_3d(tile0, tmx, tb, ld1, ld2, mbar0);
   }
   for (int i = 0; i < ntiles; ++i) {
     const int j = NG == 1 ? (i & 1) : (i & (NG - 1));   // buffer of tile i
@@ -150,14 +150,14 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
           // finished READING it (it was issued a whole barrier-wait ago, so this normally does not block).
           if (i >= 1) alz_bulk_wait_read0();
           alz_mbar_expect_tx(mbar0 + 8 * (j ^ 1), ALZ_TMA_TILE_BYTES);
-          alz_tile_load(a, tile0 + (j ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, s0, mbar0 + 8 * (j ^ 1));
+          alz_tma_load_3d(tile0 + (j ^ 1) * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + ALZ_TT, ld1, ld2, mbar0 + 8 * (j ^ 1));
         }
       } else if (j == 0) {
         if (i > 0) alz_bulk_wait_read0();
         const int n = ntiles - i < NG ? ntiles - i : NG;
         for (int jj = 0; jj < n; ++jj) {
           alz_mbar_expect_tx(mbar0 + 8 * jj, ALZ_TMA_TILE_BYTES);
-          alz_tile_load(a, tile0 + jj * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + jj * ALZ_TT, s0, mbar0 + 8 * jj);
+          alz_tma_load_3d(tile0 + jj * ALZ_TMA_TILE_BYTES, tmx, tb + t0 + jj * ALZ_TT, ld1, ld2, mbar0 + 8 * jj);
         }
       }
     }
@@ -170,12 +170,12 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
     const bool last = i + 1 == ntiles;
     if (lane == 0 && !(a.exp & 2)) {
       if (NG == 1) {
-        if (!(tail_by_lanes && last)) alz_tile_store(a, tmy, tb + t0, c, s0, tile0 + j * ALZ_TMA_TILE_BYTES);   // ragged last tile: stored after the loop
+        if (!(tail_by_lanes && last)) alz_tma_store_4d(tmy, tb + t0, st1, st2, st3, tile0 + j * ALZ_TMA_TILE_BYTES);   // ragged last tile: stored after the loop
         alz_bulk_commit();
       } else if (j == NG - 1 || last) {
         for (int jj = 0; jj <= j; ++jj)
           if (!(tail_by_lanes && last && jj == j))
-            alz_tile_store(a, tmy, tb + t0 - (j - jj) * ALZ_TT, c, s0, tile0 + jj * ALZ_TMA_TILE_BYTES);
+            alz_tma_store_4d(tmy, tb + t0 - (j - jj) * ALZ_TT, st1, st2, st3, tile0 + jj * ALZ_TMA_TILE_BYTES);
         alz_bulk_commit();
       }
     }
