@@ -27,7 +27,6 @@ PLAN_EXACT = 2
 PLAN_DESIGN_ONLY = 4
 PLAN_SEQUENTIAL = 8
 PLAN_PARALLEL = 16
-PLAN_STRICT_TIERS = 32
 
 #: every symbol include/alz_b200.h declares (tests check the library exports them all)
 SYMBOLS = (
@@ -46,7 +45,7 @@ class NativeError(RuntimeError):
 class PlanInfo(ctypes.Structure):
   _fields_ = [(n, ctypes.c_int32) for n in
               ("abi_version", "kind", "n_channels", "n_sections", "num_taps", "monic", "state_doubles", "fp64_ops",
-               "device", "n_fp32_channels", "tier_tol_e9", "n_dform_channels")] + [("reserved", ctypes.c_int32 * 4)]
+               "device", "n_fp32_channels", "tier_tol_e9")] + [("reserved", ctypes.c_int32 * 5)]
 
 
 _lib = None
@@ -145,13 +144,12 @@ def pack_sections(bank):
 class Plan(object):
   """A compiled bank of cascades living on the current CUDA device."""
 
-  def __init__(self, bank, force_generic=False, exact=False, design_only=False, sequential=False, parallel=False, strict_tiers=False):
+  def __init__(self, bank, force_generic=False, exact=False, design_only=False, sequential=False, parallel=False):
     L = lib()
     coef, desc, C, KM = pack_sections(bank)
     handle = ctypes.c_void_p()
     flags = (PLAN_FORCE_GENERIC if force_generic else 0) | (PLAN_EXACT if exact else 0) | \
-            (PLAN_DESIGN_ONLY if design_only else 0) | (PLAN_SEQUENTIAL if sequential else 0) | (PLAN_PARALLEL if parallel else 0) | \
-            (PLAN_STRICT_TIERS if strict_tiers else 0)
+            (PLAN_DESIGN_ONLY if design_only else 0) | (PLAN_SEQUENTIAL if sequential else 0) | (PLAN_PARALLEL if parallel else 0)
     _check(L.alz_plan_create_ex(coef.ctypes.data, desc.ctypes.data, C, KM, flags, ctypes.byref(handle)))
     self._h = handle
     info = PlanInfo()
@@ -165,7 +163,6 @@ class Plan(object):
     self.fp64_ops = info.fp64_ops
     self.device = info.device
     self.n_fp32_channels = info.n_fp32_channels
-    self.n_dform_channels = info.n_dform_channels
     self.tier_tol = info.tier_tol_e9 * 1e-9
     xd, yd = ctypes.c_int32(), ctypes.c_int32()
     _check(L.alz_plan_history(self._h, ctypes.byref(xd), ctypes.byref(yd)))

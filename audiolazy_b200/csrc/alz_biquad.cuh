@@ -89,18 +89,8 @@ __host__ __device__ __forceinline__ float alz_fma(float a, float b, float c) { r
 // the parity bar (alz_capi.cu: tier probe) -- high ERB channels with poles far from z = 1.  The
 // float32 warps use the FP32 pipe and no conversions, and run in the issue slots the FP64 warps
 // of the same SM leave free.
-// FORM (float32 only): 0 = direct form as above (tier 1); 1 = DIFFERENCE form (tier 2) for poles near z = 1, where the
-// direct form's float32 coefficients (2 A cos w ~ 2, A^2 ~ 1) cannot place the poles and its rounding noise is amplified
-// by 1 / |1 - p|^2.  Per section the state is (y1, d1 = y1 - y2) and
-//     w = t - h y1 - e2 d1,   d = d1 + w,   y = y1 + d,        h = 1 - 2 A cos w + A^2 = |1 - p|^2,   e2 = 1 - A^2
-// (t = the numerator part): the same transfer function, but h and e2 are SMALL numbers, so their float32 images carry
-// the pole position to 2^-24 of its distance from z = 1, and the rounding of y = y1 + d enters through (1 - A^2 z^-1) /
-// A(z): shaped away from the resonance.  Measured (tools/tier_sim.py): error <= 1.6e-6 from ERB channel 6 (190 Hz)
-// upward where the direct float32 form gives 1e-3 ... 1e-5; 5 FP32 operations per section instead of 3.  The y2 slot
-// of the state buffer holds d1 for such a channel (alz_state_init converts).
-template <int K, int NB, int MONIC, int NB0 = 0, int ZMASK = 0, typename W = double, int FORM = 0>
+template <int K, int NB, int MONIC, int NB0 = 0, int ZMASK = 0, typename W = double>
 struct AlzBiquadCore {
-  static_assert(FORM == 0 || NB0 == 0, "the difference form has no head-FIR variant");
   static constexpr int H0 = ALZ_H0(NB0);
   static constexpr int NBF = NB0 > 3 ? NB0 : NB;   // taps of section 0
   W b0[K], c1[K], c2[K], na1[K], na2[K];
@@ -184,17 +174,8 @@ struct AlzBiquadCore {
     W t = MONIC ? in : b0[k] * in;
     if (NB >= 2 && !((ZMASK >> (2 * k)) & 1)) t = alz_fma(c1[k], in1, t);
     if (NB >= 3 && !((ZMASK >> (2 * k + 1)) & 1)) t = alz_fma(c2[k], in2, t);
-    if (FORM == 1) return t;                  // difference form: the caller finishes (it needs both d and y)
     t = alz_fma(na2[k], y2, t);
     return alz_fma(na1[k], y1, t);
-  }
-
-  // difference form: (y1, d1) -> (y, d); na1[k] holds -h, na2[k] holds -e2
-  __host__ __device__ __forceinline__ W dform(int k, W t, W y1, W& d) const {
-    W w = alz_fma(na1[k], y1, t);
-    w = alz_fma(na2[k], d, w);
-    d = d + w;
-    return y1 + d;
   }
 
   // Steady state: section k reads the history of section k-1's output.
@@ -214,18 +195,10 @@ struct AlzBiquadCore {
 #pragma unroll
     for (int k = (NB0 > 3 ? 1 : 0); k < K; ++k) {
       const W y1 = u[k + 1][0], y2 = u[k + 1][1];
-      if (FORM == 1) {
-        W d = y2;                              // the slot holds d1 = y1 - y2
-        const W y = dform(k, section(k, in, in1, in2, y1, y2), y1, d);
-        u[k + 1][1] = d;
-        u[k + 1][0] = y;
-        in = y; in1 = y1; in2 = y1 - y2;       // the next section's x[n-2] (dead code unless it has that tap)
-      } else {
-        const W y = section(k, in, in1, in2, y1, y2);
-        u[k + 1][1] = y1;
-        u[k + 1][0] = y;
-        in = y; in1 = y1; in2 = y2;
-      }
+      const W y = section(k, in, in1, in2, y1, y2);
+      u[k + 1][1] = y1;
+      u[k + 1][0] = y;
+      in = y; in1 = y1; in2 = y2;
     }
     return MONIC == 1 ? G * in : in;
   }
@@ -240,18 +213,10 @@ struct AlzBiquadCore {
       if (k == 0) { in1 = u[0][0]; in2 = u[0][1]; u[0][1] = in1; u[0][0] = in; }
       else { in1 = xe[k][0]; in2 = xe[k][1]; xe[k][1] = in1; xe[k][0] = in; }
       const W y1 = u[k + 1][0], y2 = u[k + 1][1];
-      if (FORM == 1) {
-        W d = y2;
-        const W y = dform(k, section(k, in, in1, in2, y1, y2), y1, d);
-        u[k + 1][1] = d;
-        u[k + 1][0] = y;
-        in = y;
-      } else {
-        const W y = section(k, in, in1, in2, y1, y2);
-        u[k + 1][1] = y1;
-        u[k + 1][0] = y;
-        in = y;
-      }
+      const W y = section(k, in, in1, in2, y1, y2);
+      u[k + 1][1] = y1;
+      u[k + 1][0] = y;
+      in = y;
     }
     return MONIC == 1 ? G * in : in;
   }
@@ -336,7 +301,7 @@ struct AlzBiquadCore {
     for (int k = 1; k < K; ++k) {
       const int base = ALZ_STATE_BASE(k, NB0);
       W x1, x2;
-      if (T >= 2) { x1 = u[k][0]; x2 = FORM == 1 ? u[k][0] - u[k][1] : u[k][1]; }   // aliased: section k-1's output history (difference form: y2 = y1 - d1, the subtraction the steady-state loop does)
+      if (T >= 2) { x1 = u[k][0]; x2 = u[k][1]; }   // aliased: section k-1's output history
       else { x1 = xe[k][0]; x2 = xe[k][1]; }
       st[(long long)(base + 0) * R] = (double)x1;
       st[(long long)(base + 1) * R] = (double)x2;

@@ -387,53 +387,32 @@ int32_t alz_plan_create_ex(const double* coef, const int32_t* desc, int32_t C, i
     p->tier_err.assign(C, -1.0);
     p->tier_tol = env_double("ALZ_TIER_TOL", 2.5e-6);
     p->probe_len = std::max(64, env_int("ALZ_TIER_PROBE", 8192));
-    p->probe_signals = (env_int("ALZ_TIER_STRICT", 0) || (flags & ALZ_PLAN_STRICT_TIERS)) ? 5 : 4;
     const bool tiering = !(flags & ALZ_PLAN_EXACT) && !p->parallel_sum && !env_int("ALZ_NO_FP32_TIER", 0) && p->tier_tol > 0.0;
-    std::vector<double> tab32((size_t)C * stride, 0.0);   // the chosen float32 record of every channel, as packed floats
-    std::vector<double> trial((size_t)stride, 0.0);
-    const bool dform_ok = p->NB0 == 0 && !env_int("ALZ_NO_DFORM", 0);
+    std::vector<double> tab32((size_t)C * stride, 0.0);   // the same records as packed floats
     for (int c = 0; c < C; ++c) {
       const double* rec = tab.data() + (size_t)c * stride;
-      if (!tiering) continue;
-      // tier 1: the direct form in float32; tier 2: the difference form (slots 3 / 4 of a section = -h, -e2 with
-      // h = 1 - na1 - na2, e2 = 1 + na2, evaluated in float64 and THEN rounded: small numbers keep their relative precision)
-      for (int t = 1; t <= (dform_ok ? 2 : 1) && p->tier[c] == 0; ++t) {
-        float* r32 = reinterpret_cast<float*>(trial.data());
-        bool representable = true;
-        for (int i = 0; i < nval; ++i) {
-          double v = rec[i];
-          if (t == 2 && i < 5 * K && i % 5 == 3) v = -(1.0 - rec[i] - rec[i + 1]);
-          if (t == 2 && i < 5 * K && i % 5 == 4) v = -(1.0 + rec[i]);
-          r32[i] = (float)v;
-          if (v != 0.0 && !(std::fabs(v) > 1e-30 && std::fabs(v) < 1e30)) representable = false;
-        }
-        if (!representable) continue;
-        p->probe_tier = t;
-        const double err = probe_biquad(p, rec, trial.data());
-        if (t == 1 || err < p->tier_err[c] || p->tier_err[c] < 0) p->tier_err[c] = err;
-        if (err <= p->tier_tol) {
-          p->tier[c] = t;
-          p->tier_err[c] = err;
-          ++p->n_fp32;
-          if (t == 2) ++p->n_dform;
-          memcpy(tab32.data() + (size_t)c * stride, trial.data(), (size_t)nval * sizeof(double));
-        }
+      float* r32 = reinterpret_cast<float*>(tab32.data() + (size_t)c * stride);
+      bool representable = true;
+      for (int i = 0; i < nval; ++i) {
+        r32[i] = (float)rec[i];
+        if (rec[i] != 0.0 && !(std::fabs(rec[i]) > 1e-30 && std::fabs(rec[i]) < 1e30)) representable = false;
+      }
+      if (tiering && representable) {
+        p->tier_err[c] = probe_biquad(p, rec, tab32.data() + (size_t)c * stride);
+        if (p->tier_err[c] <= p->tier_tol) { p->tier[c] = 1; ++p->n_fp32; }
       }
     }
-    // ---- positions: interleave the tiers along blockIdx.x so every kind of warp shares every SM ----
+    // ---- positions: interleave the tiers along blockIdx.x so both kinds of warp share every SM ----
     {
-      std::vector<std::pair<double, int>> keyed;
-      int seen[3] = {0, 0, 0}, total[3] = {0, 0, 0};
-      for (int c = 0; c < C; ++c) ++total[p->tier[c]];
-      const int order = env_int("ALZ_TIER_ORDER", 1);   // 1: interleave the tiers evenly; 0: channel order
-      for (int c = 0; c < C; ++c) {
-        const int t = p->tier[c];
-        keyed.push_back({order == 1 ? (seen[t] + 0.5) / total[t] : (double)c, c});
-        ++seen[t];
-      }
-      std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
+      std::vector<int> lst[2];
+      const int order = env_int("ALZ_TIER_ORDER", 1);   // 1: interleave the tiers; 0: channel order; 2: float32 channels first
+      for (int c = 0; c < C; ++c) lst[order == 1 ? p->tier[c] : (order == 2 ? 1 - p->tier[c] : 0)].push_back(c);
+      size_t i0 = 0, i1 = 0;
       p->pos_channel.clear();
-      for (auto& kv : keyed) p->pos_channel.push_back(kv.second);
+      while (i0 < lst[0].size() || i1 < lst[1].size()) {   // Bresenham merge: the list that is less consumed goes next
+        const bool take0 = i1 >= lst[1].size() || (i0 < lst[0].size() && i0 * lst[1].size() <= i1 * lst[0].size());
+        p->pos_channel.push_back(take0 ? lst[0][i0++] : lst[1][i1++]);
+      }
     }
     p->h_tab.assign((size_t)C * stride, 0.0);
     for (int pos = 0; pos < C; ++pos) {
@@ -652,7 +631,6 @@ int32_t alz_plan_info_get(const alz_plan* p, alz_plan_info* out) {
   out->fp64_ops = p->fp64_ops;
   out->device = p->device;
   out->n_fp32_channels = p->n_fp32;
-  out->n_dform_channels = p->n_dform;
   out->tier_tol_e9 = (int32_t)std::min(2.0e9, p->tier_tol * 1e9 + 0.5);
   return ALZ_OK;
 }
@@ -716,12 +694,6 @@ int32_t alz_state_init(const alz_plan* p, double* state, int64_t S, const double
         for (int j = 0; j < 2; ++j) {
           const double yv = yinit ? yinit[((size_t)c * K + k) * 2 + j] : 0.0;
           proto[(size_t)(base + nx + j) * C + c] = yv * sc_out;
-        }
-        if (!p->tier.empty() && p->tier[c] == 2) {   // difference form: the y2 slot holds d1 = y1 - y2, as float32 values
-          double& y1 = proto[(size_t)(base + nx + 0) * C + c];
-          double& y2 = proto[(size_t)(base + nx + 1) * C + c];
-          y1 = (double)(float)y1;
-          y2 = (double)((float)y1 - (float)y2);
         }
       }
   } else if (p->window) {

@@ -50,10 +50,7 @@ struct alz_plan {
   int state_doubles = 0;       // per recurrence
   int fp64_ops = 0;            // FP64 instructions per channel-sample of a float64-tier channel
   int fp64_ops_exact = 0;
-  int n_fp32 = 0;              // biquad: channels on the float32 tiers (1 and 2)
-  int n_dform = 0;             // ... of which on tier 2 (difference form)
-  int probe_signals = 4;       // 4: noise, step, impulse, noise + Nyquist tone; 5 (ALZ_TIER_STRICT): also the pure Nyquist sequence
-  int probe_tier = 1;          // tier the probe functions emulate (set around the calls during plan creation)
+  int n_fp32 = 0;              // biquad: channels on the float32 tier
   double tier_tol = 0.0;       // measured-error threshold the tier decision used
   int probe_len = 8192;        // samples per probe signal of the tier decision
   int tile_group = 2;          // TMA engine: tiles moved together by launches that fill the machine (1, 2, 4)
@@ -79,7 +76,7 @@ struct alz_plan {
   // host copies used by alz_state_init
   std::vector<double> h_tab;              // biquad: [position][ALZ_COEF_STRIDE] coefficient records (kernel parameters)
   std::vector<int> pos_channel;           // biquad: position -> channel
-  std::vector<int> tier;                  // biquad: per CHANNEL precision tier (0 float64, 1 float32 direct form, 2 float32 difference form)
+  std::vector<int> tier;                  // biquad: per CHANNEL precision tier (0 float64, 1 float32)
   std::vector<double> tier_err;           // biquad: per channel measured float32 error (probe), < 0 = not probed
   std::vector<double> sc;                 // biquad: [C][K+1] working-unit scales
   std::vector<AlzGenSection> h_sec;       // generic

@@ -74,10 +74,9 @@ typedef struct alz_plan_info {
   int32_t state_doubles;     /* doubles of state per (stream, channel)                */
   int32_t fp64_ops;          /* FP64 instructions per channel-sample in the hot loop  */
   int32_t device;            /* CUDA device ordinal the plan lives on                 */
-  int32_t n_fp32_channels;   /* channels whose recurrence runs on a float32 tier (see alz_plan_tiers) */
+  int32_t n_fp32_channels;   /* channels whose recurrence runs on the float32 tier (see alz_plan_tiers) */
   int32_t tier_tol_e9;       /* the tier decision's error threshold, in units of 1e-9 */
-  int32_t n_dform_channels;  /* ... of which on tier 2, the float32 difference form */
-  int32_t reserved[4];
+  int32_t reserved[5];
 } alz_plan_info;
 
 /* Thread-local description of the last error returned on this thread. */
@@ -123,12 +122,6 @@ int32_t alz_plan_create(const double* coef, const int32_t* section_desc,
 /* ALZ_PLAN_SEQUENTIAL: never use the time-parallel evaluation (see alz_apply_f32): every call is
  * evaluated sample by sample, so ANY blocking of a stream gives the same bits. */
 #define ALZ_PLAN_SEQUENTIAL 8
-/* ALZ_PLAN_STRICT_TIERS (or ALZ_TIER_STRICT=1): the tier probe (alz_plan_tiers) also uses a PURE Nyquist
- * sequence.  A narrow low-frequency channel answers such an input 100+ dB down; the in-band rounding noise of
- * ANY float32 recurrence (~1e-7 of the input, absolute) is then large relative to that output.  The default
- * probe set (white noise, step, impulse, noise + a full-scale Nyquist tone) bounds the error for inputs that
- * have in-band content; the strict set keeps such channels in float64. */
-#define ALZ_PLAN_STRICT_TIERS 32
 /* ALZ_PLAN_PARALLEL: the plan is the member list of a ParallelFilter (reference lazy_filters.py:1024-1084):
  * plain float64 sections, every channel on the float64 tier; alz_apply_sum_f32 evaluates the sum in one kernel. */
 #define ALZ_PLAN_PARALLEL 16
@@ -144,13 +137,10 @@ int32_t alz_plan_info_get(const alz_plan* plan, alz_plan_info* out);
  * (lazy_filters.py:197-257 on Python floats); the parity bar of this path is 1e-5 relative to
  * each output row's peak for float32 I/O.  At plan creation every channel is run, on the host,
  * through the kernel's own arithmetic in float64 AND in float32 on probe signals (white noise,
- * step, impulse, noise + Nyquist tone); a channel whose float32 result stays within the threshold (default 2.5e-6 =
- * a quarter of the bar; ALZ_TIER_TOL) is evaluated in float32 on the device (FP32 pipe, no
- * conversions): tier 1 = the same direct form; failing that, tier 2 = the DIFFERENCE form (state
- * y1 and d1 = y1 - y2, coefficients |1 - p|^2 and 1 - A^2: the same transfer function with low
- * coefficient sensitivity and shaped rounding noise for poles near z = 1, 5 instead of 3 operations
- * per section), probed the same way; all others in float64 (tier 0).  The poles closest to z = 1 --
- * the lowest ERB channels -- fail both probes and stay on tier 0.  ALZ_PLAN_EXACT or ALZ_NO_FP32_TIER=1
+ * step, Nyquist); a channel whose float32 result stays within the threshold (default 2.5e-6 =
+ * a quarter of the bar; ALZ_TIER_TOL) is evaluated in float32 on the device (tier 1: FP32 pipe,
+ * no conversions), all others in float64 (tier 0).  Poles near z = 1 -- low ERB channels -- fail
+ * the probe by orders of magnitude and stay on tier 0.  ALZ_PLAN_EXACT or ALZ_NO_FP32_TIER=1
  * keep every channel on tier 0.  Fills tier[c] / probe_err[c] (measured float32 error, < 0 when
  * not probed) for c < min(cap, n_channels); returns n_channels.  Either array may be NULL.
  */

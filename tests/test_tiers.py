@@ -22,9 +22,8 @@ def fma32(a, b, c):
   return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
 
 
-def monic_emulation(bank, x, dtype, dform=None):
-  """Monic cascade of csrc/alz_biquad.cuh (gain on the float32 input), vectorised over channels. ``dform``: boolean
-  mask of the channels evaluated in the difference form (state y1, d1 = y1 - y2; coefficients h, e2)."""
+def monic_emulation(bank, x, dtype):
+  """Monic cascade of csrc/alz_biquad.cuh (gain on the float32 input), vectorised over channels."""
   C, K = len(bank), max(len(ch) for ch in bank)
   c1 = np.zeros((C, K)); na1 = np.zeros((C, K)); na2 = np.zeros((C, K)); G = np.ones(C)
   for c, ch in enumerate(bank):
@@ -35,9 +34,7 @@ def monic_emulation(bank, x, dtype, dform=None):
       na1[c, k], na2[c, k] = -a[1], -a[2]
   Gf = G.astype(f32)
   fma = fma32 if dtype is f32 else (lambda a, b, c: a * b + c)     # float64: fused vs. separate rounding is far below what is compared
-  dmask = np.zeros(C, dtype=bool) if dform is None else np.asarray(dform, dtype=bool)
-  nh, ne2 = -(1.0 - na1 - na2), -(1.0 + na2)
-  u = np.zeros((K + 1, 2, C), dtype=dtype)     # u[k+1][1] = y2 (direct form) or d1 (difference form)
+  u = np.zeros((K + 1, 2, C), dtype=dtype)
   y = np.empty((C, len(x)), dtype=f32)
   cf = lambda v: v.astype(dtype)
   for n in range(len(x)):
@@ -46,15 +43,13 @@ def monic_emulation(bank, x, dtype, dform=None):
     u[0, 1] = in1
     u[0, 0] = inp
     for k in range(K):
-      y1, s2 = u[k + 1, 0].copy(), u[k + 1, 1].copy()
+      y1, y2 = u[k + 1, 0].copy(), u[k + 1, 1].copy()
       t = fma(cf(c1[:, k]), in1, inp)
-      o_dir = fma(cf(na1[:, k]), y1, fma(cf(na2[:, k]), s2, t))
-      w = fma(cf(ne2[:, k]), s2, fma(cf(nh[:, k]), y1, t))
-      d = (s2 + w).astype(dtype)
-      o_dif = (y1 + d).astype(dtype)
-      u[k + 1, 1] = np.where(dmask, d, y1)
-      u[k + 1, 0] = np.where(dmask, o_dif, o_dir)
-      inp, in1 = u[k + 1, 0].copy(), y1
+      t = fma(cf(na2[:, k]), y2, t)
+      o = fma(cf(na1[:, k]), y1, t)
+      u[k + 1, 1] = y1
+      u[k + 1, 0] = o
+      inp, in1 = o, y1
     y[:, n] = inp.astype(f32)
   return y
 
@@ -64,23 +59,17 @@ def test_tier_probe_matches_an_independent_emulation(designs):
   plan = _capi.Plan(bank, design_only=True)
   assert plan.kind == _capi.KIND_BIQUAD and plan.device == -1
   tier, probe = plan.tiers()
-  assert plan.n_fp32_channels == int((tier > 0).sum()) > 0 and plan.n_dform_channels == int((tier == 2).sum()) > 0
-  assert np.all(probe[tier > 0] <= plan.tier_tol) and np.all(probe[tier == 0] > plan.tier_tol)
+  assert plan.n_fp32_channels == int(tier.sum()) > 0
+  assert np.all(probe[tier == 1] <= plan.tier_tol) and np.all(probe[tier == 0] > plan.tier_tol)
   x = lcg_noise(8192)
   y64 = monic_emulation(bank, x, np.float64).astype(np.float64)
-  peak = np.max(np.abs(y64), axis=1)
-  err_dir = np.max(np.abs(monic_emulation(bank, x, f32).astype(np.float64) - y64), axis=1) / peak
-  err_dif = np.max(np.abs(monic_emulation(bank, x, f32, dform=np.ones(len(bank), bool)).astype(np.float64) - y64), axis=1) / peak
-  # the probe also runs a step, an impulse and noise + Nyquist tone, so it may only be larger than the noise-only figure
-  mine = np.where(tier == 2, err_dif, np.where(tier == 1, err_dir, np.minimum(err_dir, err_dif)))
-  assert np.all(probe >= mine * 0.98)
-  assert np.median(probe[tier > 0] / mine[tier > 0]) < 1.3
-  # the picture: the direct form in float32 only holds for the upper channels, the difference form reaches far down,
-  # the lowest channels stay in float64
-  assert not tier[:4].any() and np.all(tier[-16:] == 1) and (tier == 2).sum() >= 20
-  assert err_dir[:16].min() > 2e-5 and err_dif[12:40].max() < 2.5e-6
-  strict = _capi.Plan(bank, design_only=True, strict_tiers=True)   # + the pure Nyquist sequence
-  assert strict.n_fp32_channels < plan.n_fp32_channels and strict.n_dform_channels <= 4
+  y32 = monic_emulation(bank, x, f32).astype(np.float64)
+  err = np.max(np.abs(y32 - y64), axis=1) / np.max(np.abs(y64), axis=1)
+  # the probe also runs a step and the Nyquist sequence, so it may only be larger; on most channels noise dominates
+  assert np.all(probe >= err * 0.98)
+  assert np.median(probe / err) < 1.05
+  # monotone picture: the 16 lowest channels are orders of magnitude outside, the top 16 well inside
+  assert probe[:16].min() > 2e-5 and probe[-16:].max() < 1.5e-6
 
 
 def test_design_only_plans_cannot_compute(designs):
