@@ -137,8 +137,11 @@ static int launch_headfir_k(const alz_plan* p, const AlzTileArgs& ta, cudaStream
 // ---- plan-time tier probe (host) -------------------------------------------------------------
 // Runs ONE channel through the float64 core and through the float32 core -- the very code the
 // kernels execute (fma / fmaf are correctly rounded on the host as on the device) -- on three
-// deterministic probe signals (uniform white noise, a unit step, the Nyquist sequence) from a
-// zero state, and returns max over the signals of max|y32 - y64| / max|y64|.
+// deterministic probe signals from a zero state -- uniform white noise; a unit step; a unit impulse;
+// white noise with a full-scale Nyquist tone on top; the pure Nyquist sequence (a narrow low channel
+// answers it 100+ dB down: any float32 recurrence's in-band rounding noise is then large relative to
+// THAT output, and such a channel stays in float64) -- and returns max over the signals of
+// max|y32 - y64| / max|y64|.
 static inline float alzi_probe_noise(unsigned& s) {   // uniform in [-1, 1), LCG (Numerical Recipes constants)
   s = s * 1664525u + 1013904223u;
   return (float)((double)(s >> 8) * (2.0 / 16777216.0) - 1.0);
@@ -147,7 +150,7 @@ static inline float alzi_probe_noise(unsigned& s) {   // uniform in [-1, 1), LCG
 template <int K, int NB, int MONIC, int NB0, int ZMASK>
 static double probe_biquad_t(const double* rec64, const double* rec32, int n) {
   double worst = 0.0;
-  for (int sig = 0; sig < 3; ++sig) {
+  for (int sig = 0; sig < 5; ++sig) {
     AlzBiquadCore<K, NB, MONIC, NB0, ZMASK, double> c64;
     AlzBiquadCore<K, NB, MONIC, NB0, ZMASK, float> c32;
     c64.load_coef(rec64); c64.zero_state();
@@ -155,7 +158,9 @@ static double probe_biquad_t(const double* rec64, const double* rec32, int n) {
     unsigned seed = 12345u;
     double peak = 0.0, err = 0.0;
     for (int i = 0; i < n; ++i) {
-      const float x = sig == 0 ? alzi_probe_noise(seed) : (sig == 1 ? 1.0f : ((i & 1) ? -1.0f : 1.0f));
+      const float nyq = (i & 1) ? -1.0f : 1.0f;
+      const float x = sig == 0 ? alzi_probe_noise(seed) : sig == 1 ? 1.0f : sig == 2 ? (i == 0 ? 1.0f : 0.0f)
+                      : sig == 3 ? 0.5f * alzi_probe_noise(seed) + 0.5f * nyq : nyq;
       float y64, y32;
       if (i < 2) { y64 = c64.step_explicit(c64.widen(x)); y32 = c32.step_explicit(c32.widen(x)); }
       else { y64 = c64.step_alias(c64.widen(x)); y32 = c32.step_alias(c32.widen(x)); }

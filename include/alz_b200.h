@@ -137,7 +137,7 @@ int32_t alz_plan_info_get(const alz_plan* plan, alz_plan_info* out);
  * (lazy_filters.py:197-257 on Python floats); the parity bar of this path is 1e-5 relative to
  * each output row's peak for float32 I/O.  At plan creation every channel is run, on the host,
  * through the kernel's own arithmetic in float64 AND in float32 on probe signals (white noise,
- * step, Nyquist); a channel whose float32 result stays within the threshold (default 2.5e-6 =
+ * step, impulse, noise + Nyquist tone, pure Nyquist); a channel whose float32 result stays within the threshold (default 2.5e-6 =
  * a quarter of the bar; ALZ_TIER_TOL) is evaluated in float32 on the device (tier 1: FP32 pipe,
  * no conversions), all others in float64 (tier 0).  Poles near z = 1 -- low ERB channels -- fail
  * the probe by orders of magnitude and stay on tier 0.  ALZ_PLAN_EXACT or ALZ_NO_FP32_TIER=1

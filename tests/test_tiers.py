@@ -65,9 +65,9 @@ def test_tier_probe_matches_an_independent_emulation(designs):
   y64 = monic_emulation(bank, x, np.float64).astype(np.float64)
   y32 = monic_emulation(bank, x, f32).astype(np.float64)
   err = np.max(np.abs(y32 - y64), axis=1) / np.max(np.abs(y64), axis=1)
-  # the probe also runs a step and the Nyquist sequence, so it may only be larger; on most channels noise dominates
+  # the probe also runs a step, an impulse, noise + a Nyquist tone and the Nyquist sequence, so it may only be larger; on most channels noise dominates
   assert np.all(probe >= err * 0.98)
-  assert np.median(probe / err) < 1.05
+  assert np.median(probe / err) < 1.25
   # monotone picture: the 16 lowest channels are orders of magnitude outside, the top 16 well inside
   assert probe[:16].min() > 2e-5 and probe[-16:].max() < 1.5e-6
 
