@@ -166,6 +166,10 @@ class LinearFilter(LinearFilterProperties):
       den = [(p, as_source(c)) for p, c in self.denpoly.terms()]
       return _engine.filter_stream_tv(num, den, seq, yinit[0], float(zero))
     sections = self.sections()
+    (b, a), = sections
+    if not any(b) and not any(a[1:]):
+      # nothing to sum: the reference's generated loop yields `zero` for every input sample (lazy_filters.py:224-228)
+      return Stream(zero for _ in seq)
     xinit, yinit = _seed_histories(sections, memory, zero)
     return _engine.filter_stream([sections], seq, [xinit], [yinit])
 
@@ -208,21 +212,19 @@ class LinearFilter(LinearFilterProperties):
     return type(self)(self.numpoly.copy(), self.denpoly.copy())
 
   def linearize(self):
-    """Replace fractional delays by linear interpolation of the two neighbours."""
-    data = []
-    for poly in (self.numpoly, self.denpoly):
-      new = {}
-      for k, v in poly.terms():
-        if isinstance(k, int) or (isinstance(k, float) and k.is_integer()):
-          pairs = [(int(k), v)]
-        else:
-          left = int(k)
-          w_right = k - left
-          pairs = [(left, v * (1. - w_right)), (left + 1, v * w_right)]
-        for key, value in pairs:
-          new[key] = new[key] + value if key in new else value
-      data.append(new)
-    return self.__class__(*data)
+    """Fractional delays become their two integer neighbours, weighted linearly: a term ``v * z**-(m + f)`` with
+    ``0 < f < 1`` is replaced by ``v (1 - f) z**-m + v f z**-(m+1)``; terms that land on the same delay add up
+    (reference ``lazy_filters.py:339-373``; e.g. ``(z ** -4.3).linearize()`` is ``0.7 z^-4 + 0.3 z^-5``)."""
+    def spread(poly):
+      out = {}
+      for power, coeff in poly.terms():
+        whole = int(power)
+        frac = power - whole
+        shares = [(whole, coeff)] if frac == 0 else [(whole, coeff * (1. - frac)), (whole + 1, coeff * frac)]
+        for delay, share in shares:
+          out[delay] = out[delay] + share if delay in out else share
+      return out
+    return self.__class__(spread(self.numpoly), spread(self.denpoly))
 
   @property
   def poles(self):
@@ -302,23 +304,34 @@ class ZFilter(LinearFilter):
     return ZFilter(+self.numpoly, self.denpoly)
 
   def diff(self, n=1, mul_after=1):
-    """n-th derivative with respect to ``z``, multiplying by ``mul_after`` after each
-    differentiation (reference ``lazy_filters.py:819-838``)."""
+    """``n``-th derivative with respect to ``z``; after each differentiation the result is multiplied by
+    ``mul_after`` (a number or a ZFilter), as ``gammatone.sampled`` needs with ``mul_after=-z`` (reference
+    ``lazy_filters.py:819-838``).
+
+    Quotient rule, kept in the form ``N_m / D**(m+1)``: with ``H_m = N_m / D**m``,
+    ``H_m' = (N_m' D - m N_m D') / D**(m+1)``, so ``N_{m+1} = mul_after (N_m' D - m N_m D')`` and only the numerator is
+    carried through the loop; the denominator is ``D**(n+1)`` at the end."""
     if isinstance(mul_after, ZFilter):
-      den = ZFilter(self.denpoly)
-      return reduce(lambda num, order: mul_after * (num.diff() * den - order * num * den.diff()),
-                    range(1, n + 1), ZFilter(self.numpoly)) / den ** (n + 1)
-    inv_sign = Poly({-1: 1})   # the polynomial variable is z**-1
-    den = self.denpoly(inv_sign)
-    return ZFilter(reduce(lambda num, order: mul_after * (num.diff() * den - order * num * den.diff()),
-                          range(1, n + 1), self.numpoly(inv_sign))(inv_sign),
-                   self.denpoly ** (n + 1))
+      carried, base = ZFilter(self.numpoly), ZFilter(self.denpoly)
+      for m in range(1, n + 1):
+        carried = mul_after * (carried.diff() * base - m * carried * base.diff())
+      return carried / base ** (n + 1)
+    to_z = Poly({-1: 1})                       # the polynomials are in z**-1: substitute to differentiate in z
+    carried, base = self.numpoly(to_z), self.denpoly(to_z)
+    for m in range(1, n + 1):
+      carried = mul_after * (carried.diff() * base - m * carried * base.diff())
+    return ZFilter(carried(to_z), self.denpoly ** (n + 1))
 
   def __call__(self, seq, memory=None, zero=0.):
-    """Filter an iterable, or substitute another ZFilter for ``z`` (composition)."""
+    """Filter an iterable; given another ZFilter ``g`` instead, return the composition ``H(g)``: every ``z**-k``
+    of both polynomials becomes ``g**-k`` (reference ``lazy_filters.py:885-887``)."""
     if isinstance(seq, ZFilter):
-      return sum(v * seq ** -k for k, v in self.numpoly.terms()) / \
-             sum(v * seq ** -k for k, v in self.denpoly.terms())
+      def at(poly):
+        total = 0
+        for power, coeff in poly.terms():
+          total = total + coeff * seq ** -power
+        return total
+      return at(self.numpoly) / at(self.denpoly)
     return super(ZFilter, self).__call__(seq, memory=memory, zero=zero)
 
   def __repr__(self):
