@@ -32,7 +32,7 @@ PLAN_PARALLEL = 16
 SYMBOLS = (
   "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_create_ex",
   "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32", "alz_plan_tiers", "alz_apply_f32_ex", "alz_host_alloc",
-  "alz_host_free", "alz_apply_sum_f32",
+  "alz_host_free", "alz_apply_sum_f32", "alz_apply_envelope_f32", "alz_apply_envelope_f32_host",
   "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
   "alz_apply_f32_host", "alz_sum_channels_f32", "alz_freq_response_f64", "alz_launch_count",
 )
@@ -98,6 +98,11 @@ def lib():
   L.alz_apply_f32_ex.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp]
   L.alz_apply_sum_f32.restype = i32
   L.alz_apply_sum_f32.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, vp]
+  f64 = ctypes.c_double
+  L.alz_apply_envelope_f32.restype = i32
+  L.alz_apply_envelope_f32.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, f64, f64, vp]
+  L.alz_apply_envelope_f32_host.restype = i32
+  L.alz_apply_envelope_f32_host.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, f64, f64]
   L.alz_host_alloc.restype = i32
   L.alz_host_alloc.argtypes = [ctypes.POINTER(vp), i64, i32, ctypes.POINTER(i32)]
   L.alz_host_free.restype = i32
@@ -195,6 +200,32 @@ class Plan(object):
     (ALZ_ERR_UNSUPPORTED) for unaligned rows or non-biquad members."""
     _check(lib().alz_apply_sum_f32(self._h, x_ptr, out_ptr, state_ptr, int(n_streams), int(n_samples), int(x_stride),
                                    int(out_stride), stream))
+
+  ENVELOPE_MODES = {"abs": 0, "squared": 1, "rms": 2}
+
+  def apply_envelope(self, x_ptr, env_ptr, state_ptr, env_state_ptr, n_streams, n_samples, x_stride, env_stride, decim,
+                     mode, g, R, stream=0):
+    """Bank + fused envelope consumer on device buffers (``alz_apply_envelope_f32``)."""
+    _check(lib().alz_apply_envelope_f32(self._h, x_ptr, env_ptr, state_ptr, env_state_ptr, int(n_streams), int(n_samples),
+                                        int(x_stride), int(env_stride), int(decim), self.ENVELOPE_MODES[mode], float(g),
+                                        float(R), stream))
+
+  def apply_envelope_host(self, x, env=None, decim=48, mode="abs", g=None, R=None):
+    """``x``: float32 ndarray [S][T] on the host -> ``env`` [S][C][T // decim]: the bank's channel envelopes
+    (``mode``: abs / squared / rms; one-pole lowpass ``e = g r + R e1``), decimated on the device."""
+    x = np.asarray(x, dtype=np.float32)
+    if x.ndim == 1:
+      x = x[None, :]
+    S, T = x.shape
+    if g is None or R is None:
+      R = 0.99 if R is None else R
+      g = 1.0 - R if g is None else g
+    if env is None:
+      env = np.empty((S, self.n_channels, T // decim), dtype=np.float32)
+    assert env.dtype == np.float32 and env.shape == (S, self.n_channels, T // decim) and env.flags.c_contiguous
+    _check(lib().alz_apply_envelope_f32_host(self._h, x.ctypes.data, env.ctypes.data, S, T, x.strides[0] // 4 if S > 1 else T,
+                                             T // decim, int(decim), self.ENVELOPE_MODES[mode], float(g), float(R)))
+    return env
 
   def tiers(self):
     """``(tier int32[C], probe_err float64[C])``: precision tier of every channel (0 float64, 1 float32) and the

@@ -100,6 +100,37 @@ class FilterBank(list):
     ``lazy_filters.py:267-301``, batched over the bank)."""
     return self.device_bank().freq_response(np.asarray(freqs, dtype=np.float64)).cpu().numpy()
 
+  # -- fused consumer --------------------------------------------------------------------
+  @staticmethod
+  def _envelope_pole(cutoff):
+    from .filters import lowpass
+    (b, a), = lowpass(cutoff).sections()      # the reference's envelope lowpass (lazy_analysis.py:440-520, lowpass.pole)
+    if len(b) != 1 or len(a) != 2:
+      raise NotImplementedError("the fused envelope uses a one-pole lowpass")
+    return b[0] / a[0], -a[1] / a[0]
+
+  def envelope(self, x, cutoff=np.pi / 512, decim=48, mode="abs"):
+    """Channel envelopes of a CUDA float32 batch ``x[S, T]`` -> ``[S, C, T // decim]``: ``envelope.<mode>`` (abs /
+    squared / rms, reference ``lazy_analysis.py:440-520``) of every channel output, decimated by ``decim`` -- rectifier,
+    lowpass and decimation run inside the bank kernel, the channel signals never reach memory."""
+    torch = _engine.torch_mod()
+    db = self.device_bank()
+    S, T = x.shape
+    g, R = self._envelope_pole(cutoff)
+    x = x.contiguous()
+    env = torch.empty((S, len(self), T // decim), dtype=torch.float32, device=x.device)
+    state = torch.zeros(max(1, db.plan.state_doubles(S)), dtype=torch.float64, device=x.device)
+    env_state = torch.zeros(S * len(self), dtype=torch.float64, device=x.device)
+    db.plan.apply_envelope(x.data_ptr(), env.data_ptr(), state.data_ptr(), env_state.data_ptr(), S, T, T, T // decim, decim,
+                           mode, g, R, torch.cuda.current_stream(x.device).cuda_stream)
+    return env
+
+  def envelope_host(self, x, cutoff=np.pi / 512, decim=48, mode="abs", out=None):
+    """:meth:`envelope` through host buffers (``alz_apply_envelope_f32_host``): a host caller receives ``256 / decim``
+    bytes per input sample instead of the bank's 256."""
+    g, R = self._envelope_pole(cutoff)
+    return self.device_bank().plan.apply_envelope_host(x, out, decim=decim, mode=mode, g=g, R=R)
+
   def apply_host(self, x, out=None, state=None):
     """``x``: float32 ndarray ``[S, T]`` (or ``[T]``) on the host; returns ndarray ``[S, C, T]``.
     Goes through ``alz_apply_f32_host`` (pipelined H2D / kernel / D2H)."""

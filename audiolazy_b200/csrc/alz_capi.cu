@@ -972,6 +972,93 @@ int32_t alz_apply_f32_ex(const alz_plan* p, const float* x, float* y, double* st
   return rc;
 }
 
+static int envelope_impl(const alz_plan* p, const float* x, float* env, double* state, double* env_state, long long sstride,
+                         long long S, long long T, long long xs, long long es, int decim, int mode, double g, double R,
+                         cudaStream_t st) {
+  AlzTileArgs ta{};
+  ta.x = x; ta.y = env;                      // y only feeds the (unused) output tensor map: any valid 16-byte aligned address
+  ta.S = S; ta.T = T; ta.xs = xs; ta.ys = (T + 3) & ~3LL; ta.ysS = (long long)p->C * ta.ys; ta.C = p->C; ta.Stot = sstride / p->C;
+  ta.state = state; ta.sstride = sstride;
+  ta.vec_in = (((uintptr_t)x & 15) == 0 && (xs & 3) == 0) ? 1 : 0;
+  ta.vec_out = 1;
+  ta.env_out = env; ta.env_es = es; ta.env_state = env_state; ta.env_g = g; ta.env_R = R; ta.env_decim = decim; ta.env_mode = mode;
+  return p->NB0 == 8 ? alzi_launch_envelope_headfir_k4(p, ta, st) : alzi_launch_envelope_k4(p, ta, st);
+}
+
+static int envelope_check(const alz_plan* p, int64_t S, int64_t T, int64_t xs, int64_t es, int32_t decim, int32_t mode) {
+  if (!p) return fail(ALZ_ERR_INVALID, "plan is null");
+  if (p->device < 0) return fail(ALZ_ERR_CUDA, "design-only plan: no device");
+  if (S < 0 || T < 0 || decim < 1 || mode < 0 || mode > 2) return fail(ALZ_ERR_INVALID, "bad argument");
+  if (T % decim) return fail(ALZ_ERR_INVALID, "n_samples must be a multiple of the decimation factor");
+  if (xs < T || es < T / decim) return fail(ALZ_ERR_INVALID, "row stride shorter than the row");
+  if (p->kind != ALZ_KIND_BIQUAD || p->K != 4 || p->monic != 2 || S > 65535ll * 32)
+    return fail(ALZ_ERR_UNSUPPORTED, "the envelope consumer is built for the gammatone banks (4 sections per channel)");
+  return ALZ_OK;
+}
+
+int32_t alz_apply_envelope_f32(const alz_plan* p, const float* x, float* env, double* state, double* env_state, int64_t S,
+                               int64_t T, int64_t xs, int64_t es, int32_t decim, int32_t mode, double g, double R,
+                               void* cuda_stream) {
+  const int chk = envelope_check(p, S, T, xs, es, decim, mode);
+  if (chk != ALZ_OK) return chk;
+  if (S == 0 || T == 0) return ALZ_OK;
+  if (!x || !env || !state || !env_state) return fail(ALZ_ERR_INVALID, "null buffer");
+  int cur = -1;
+  ALZ_CUDA(cudaGetDevice(&cur));
+  if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));
+  const int rc = envelope_impl(p, x, env, state, env_state, (long long)S * p->C, S, T, xs, es, decim, mode, g, R, (cudaStream_t)cuda_stream);
+  if (cur != p->device) cudaSetDevice(cur);
+  return rc;
+}
+
+int32_t alz_apply_envelope_f32_host(const alz_plan* cp, const float* xh, float* eh, int64_t S, int64_t T, int64_t xs, int64_t es,
+                                    int32_t decim, int32_t mode, double g, double R) {
+  alz_plan* p = const_cast<alz_plan*>(cp);
+  const int chk = envelope_check(p, S, T, xs, es, decim, mode);
+  if (chk != ALZ_OK) return chk;
+  if (S == 0 || T == 0) return ALZ_OK;
+  if (!xh || !eh) return fail(ALZ_ERR_INVALID, "null buffer");
+  std::lock_guard<std::mutex> lock(p->host_mu);
+  ALZ_CUDA(cudaSetDevice(p->device));
+  const long long C = p->C, Td = T / decim, Tp = (T + 3) & ~3LL, Tdp = (Td + 3) & ~3LL;
+  // chunks of whole streams: <= 64 MiB of input per chunk (the output is decim times smaller than the bank's)
+  long long Sc = std::max<long long>(32, (64LL << 20) / (Tp * 4) / 32 * 32);
+  if (Sc > S) Sc = S;
+  const int NB = AlzHostPipe::NBUF;
+  cudaStream_t stream[NB];
+  float *dx[NB] = {}, *de[NB] = {};
+  double *dst[NB] = {}, *des[NB] = {};
+  int rc = ALZ_OK;
+  for (int i = 0; i < NB; ++i) {
+    ALZ_CUDA(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
+    ALZ_CUDA(cudaMalloc(&dx[i], (size_t)Sc * Tp * 4));
+    ALZ_CUDA(cudaMalloc(&de[i], (size_t)Sc * C * Tdp * 4));
+    ALZ_CUDA(cudaMalloc(&dst[i], (size_t)p->state_doubles * Sc * C * 8));
+    ALZ_CUDA(cudaMalloc(&des[i], (size_t)Sc * C * 8));
+  }
+  int i = 0;
+  for (long long s0 = 0; s0 < S && rc == ALZ_OK; s0 += Sc, ++i) {
+    const long long n = std::min<long long>(Sc, S - s0);
+    const int b = i % NB;
+    cudaStream_t st = stream[b];
+    cudaMemsetAsync(dst[b], 0, (size_t)p->state_doubles * n * C * 8, st);
+    cudaMemsetAsync(des[b], 0, (size_t)n * C * 8, st);
+    cudaError_t e = cudaMemcpy2DAsync(dx[b], Tp * 4, xh + s0 * xs, xs * 4, T * 4, n, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
+    rc = envelope_impl(p, dx[b], de[b], dst[b], des[b], n * C, n, T, Tp, Tdp, decim, mode, g, R, st);
+    if (rc != ALZ_OK) break;
+    e = cudaMemcpy2DAsync(eh + s0 * C * es, es * 4, de[b], Tdp * 4, Td * 4, n * C, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
+  }
+  for (int k = 0; k < NB; ++k) {
+    cudaError_t e = cudaStreamSynchronize(stream[k]);
+    if (e != cudaSuccess && rc == ALZ_OK) rc = fail(ALZ_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
+    cudaFree(dx[k]); cudaFree(de[k]); cudaFree(dst[k]); cudaFree(des[k]);
+    cudaStreamDestroy(stream[k]);
+  }
+  return rc;
+}
+
 int32_t alz_apply_sum_f32(const alz_plan* p, const float* x, float* out, double* state, int64_t S, int64_t T,
                           int64_t xs, int64_t os, void* cuda_stream) {
   if (!p) return fail(ALZ_ERR_INVALID, "plan is null");

@@ -65,7 +65,41 @@ __device__ __forceinline__ void alz_bulk_wait_read0() { asm volatile("cp.async.b
 __device__ __forceinline__ void alz_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void alz_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-template <class Core, class CoreArgs>
+// Consumers of a filtered tile.  AlzStoreY (default): the tile goes to y[S][C][T] by TMA.  AlzEnvelopePost: the tile is
+// consumed in place -- rectifier / squarer, float64 one-pole lowpass (reference lazy_analysis.py:440-520: envelope.abs /
+// .squared / .rms = lowpass(cutoff)(abs(sig)) ...), decimation -- and only every env_decim-th envelope value leaves the SM:
+// the 256 B per input sample of the bank's output shrink to 256 / env_decim.
+struct AlzStoreY {
+  static constexpr bool active = false;
+};
+struct AlzEnvelopePost {
+  static constexpr bool active = true;
+  double env;
+  float* out;          // next output slot of this lane's (stream, channel) row
+  double* st;
+  int left;            // samples until the next kept value
+  __device__ __forceinline__ void load(const AlzTileArgs& a, int c, long long s, long long r, long long tbeg) {
+    st = a.env_state + r;
+    env = __ldcg(st);
+    out = a.env_out + (s * a.C + c) * a.env_es + tbeg / a.env_decim;
+    left = a.env_decim - (int)(tbeg % a.env_decim);
+  }
+  __device__ __forceinline__ void tile(const AlzTileArgs& a, const float* row, int swz, int nvalid, bool valid) {
+    for (int j = 0; j < nvalid; ++j) {
+      const float y = row[(((j >> 2) ^ swz) << 2) | (j & 3)];
+      const double r = a.env_mode == 0 ? (double)fabsf(y) : (double)y * (double)y;
+      env = fma(a.env_R, env, a.env_g * r);
+      if (--left == 0) {
+        if (valid) *out = (float)(a.env_mode == 2 ? sqrt(env) : env);
+        ++out;
+        left = a.env_decim;
+      }
+    }
+  }
+  __device__ __forceinline__ void store() { *st = env; }
+};
+
+template <class Core, class Post = AlzStoreY, class CoreArgs>
 __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const CoreArgs& ca, const CUtensorMap* tmx,
                                                  const CUtensorMap* tmy, unsigned char* smem) {
   const int lane = threadIdx.x;
@@ -118,6 +152,8 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
 
   Core core;
   core.load(a, ca, r, c_local, valid);
+  Post post;
+  if constexpr (Post::active) post.load(a, c, valid ? s : a.S - 1, r, tbeg);
 
   const int ntiles = (int)((tlen + ALZ_TT - 1) / ALZ_TT);
   const int nfull = (int)(tlen / ALZ_TT);
@@ -165,10 +201,11 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
       alz_mbar_wait(mbar0 + 8 * j, (NG == 1 ? (i >> 1) : (i >> lg)) & 1);   // tile i has landed (async proxy writes visible after the wait)
     const int nvalid = i < nfull ? ALZ_TT : (int)(tlen - t0);
     core.tile(myrow + j * (ALZ_TMA_TILE_BYTES / 4), swz, nvalid, t0);
+    if constexpr (Post::active) post.tile(a, myrow + j * (ALZ_TMA_TILE_BYTES / 4), swz, nvalid, valid);
     alz_fence_async_smem();                          // my generic-proxy writes -> visible to the TMA store
     __syncwarp();
     const bool last = i + 1 == ntiles;
-    if (lane == 0 && !(a.exp & 2)) {
+    if (lane == 0 && !(a.exp & 2) && !Post::active) {
       if (NG == 1) {
         if (!(tail_by_lanes && last)) alz_tma_store_4d(tmy, tb + t0, st1, st2, st3, tile0 + j * ALZ_TMA_TILE_BYTES);   // ragged last tile: stored after the loop
         alz_bulk_commit();
@@ -181,7 +218,7 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
     }
     last_buf = j;
   }
-  if (tail_by_lanes && valid) {
+  if (tail_by_lanes && valid && !Post::active) {
     // The TMA clips a box at 16-byte granularity: when n_samples is not a multiple of 4 the ragged
     // last tile is written by the lanes themselves (plain stores of the valid samples only).
     const int i = ntiles - 1, t0 = i * ALZ_TT, nvalid = (int)(tlen - t0);
@@ -191,6 +228,7 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
   }
   if (lane == 0) alz_bulk_wait0();                   // all output tiles are globally written before exit
   if (valid) core.store(a, r, tlen);
+  if constexpr (Post::active) { if (valid) post.store(); }
   if (flag != nullptr && seg + 1 < a.nseg) {         // hand the state to the next segment
     __threadfence();
     __syncwarp();

@@ -40,6 +40,36 @@ alz_biquad_tma_kernel(const __grid_constant__ AlzTileArgs a, const __grid_consta
     alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK, float>>(a, ca, &tmx, &tmy, alz_smem_tma);
 }
 
+// Envelope consumer (AlzEnvelopePost): the bank's outputs are rectified / squared, lowpassed and decimated in the kernel;
+// instantiated for the gammatone banks only (K = 4, input-side gain, one parameter block).
+template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>
+__global__ void __launch_bounds__(32, kWarpsPerSmTma)
+alz_biquad_envelope_kernel(const __grid_constant__ AlzTileArgs a, const __grid_constant__ AlzBiquadArgs<NCOEF> ca,
+                           const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy) {
+  extern __shared__ __align__(1024) unsigned char alz_smem_tma[];
+  if (ca.tier(blockIdx.x) == 0)
+    alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK, double>, AlzEnvelopePost>(a, ca, &tmx, &tmy, alz_smem_tma);
+  else
+    alz_run_warp_tma<AlzBiquadCore<K, NB, MONIC, NB0, ZMASK, float>, AlzEnvelopePost>(a, ca, &tmx, &tmy, alz_smem_tma);
+}
+
+template <int K, int NB, int NB0, int ZMASK>
+static int launch_envelope_t(const alz_plan* p, AlzTileArgs ta, cudaStream_t st) {
+  if (p->monic != 2 || p->coef_small || p->chunks.size() != 1)
+    return alzi_fail(ALZI_ERR_UNSUPPORTED, "envelope consumer: gammatone-bank plans only");
+  CUtensorMap tmx, tmy;
+  if (!alzi_make_tensor_maps(ta, &tmx, &tmy)) return alzi_fail(ALZI_ERR_UNSUPPORTED, "envelope consumer needs 16-byte aligned x rows");
+  const long long groups = (ta.S + 31) / 32;
+  ta.paired = (long long)p->chunks[0].npos * groups >= (long long)p->sm_count * kWarpsPerSmTma ? 2 : 1;
+  ta.groups = (int)groups;
+  void* args[4] = {(void*)&ta, p->chunks[0].block, (void*)&tmx, (void*)&tmy};
+  ALZ_CUDA(cudaLaunchKernel((const void*)alz_biquad_envelope_kernel<K, NB, 2, kCoefLarge, NB0, ZMASK>,
+                            dim3((unsigned)p->chunks[0].npos, (unsigned)groups), dim3(32), args, ALZ_TMA_SMEM_FOR(ta.paired), st));
+  ALZ_CUDA(cudaGetLastError());
+  alzi_launches.fetch_add(1, std::memory_order_relaxed);
+  return ALZI_OK;
+}
+
 // One launch: positions [p0, p0+npos) x stream groups of `ta` (ta.S <= 65535*32 streams).  `block` is
 // the plan's pre-built AlzBiquadArgs<NCOEF> for this chunk.
 template <int K, int NB, int MONIC, int NCOEF, int NB0, int ZMASK>

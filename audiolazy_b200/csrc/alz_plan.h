@@ -105,6 +105,8 @@ int alzi_launch_biquad_k8(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 int alzi_launch_headfir_k1(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 int alzi_launch_headfir_k4(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 
+int alzi_launch_envelope_k4(const alz_plan*, const AlzTileArgs&, cudaStream_t);
+int alzi_launch_envelope_headfir_k4(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 int alzi_launch_window(const alz_plan*, const AlzTileArgs&, cudaStream_t);
 int alzi_launch_parallel(const alz_plan*, const AlzTileArgs&, const CUtensorMap& tmx, const CUtensorMap& tmo, cudaStream_t);
 size_t alzi_window_block_bytes(bool small);

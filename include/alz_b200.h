@@ -221,6 +221,23 @@ int32_t alz_apply_f32_host(const alz_plan* plan, const float* x_host, float* y_h
                            int64_t x_stride, int64_t y_stride);
 
 /*
+ * The bank with a fused envelope consumer (reference lazy_analysis.py:440-520: envelope.abs / .squared / .rms are
+ * lowpass(cutoff)(abs(sig)), lowpass(cutoff)(sig ** 2), (...) ** .5): every channel output y is rectified (mode 0: |y|)
+ * or squared (mode 1; mode 2 = squared, square root on output), followed by the one-pole lowpass
+ * e[n] = g r[n] + R e[n-1] in float64, and only every decim-th value is stored: env_dev[s][c][n / decim].  The bank's
+ * 256 bytes of output per input sample never leave the SM; a host caller receives 256 / decim bytes per input sample.
+ * Same values as alz_apply_f32 followed by that lowpass on the float32 y.  For gammatone-bank plans (4 sections per
+ * channel); n_samples % decim == 0; x rows 16-byte aligned.  env_state_dev: n_channels * n_streams doubles (in/out),
+ * state_dev as alz_apply_f32.  The _host variant takes host buffers (zero initial state), copies inside, synchronous.
+ */
+int32_t alz_apply_envelope_f32(const alz_plan* plan, const float* x_dev, float* env_dev, double* state_dev,
+                               double* env_state_dev, int64_t n_streams, int64_t n_samples, int64_t x_stride,
+                               int64_t env_stride, int32_t decim, int32_t mode, double g, double R, void* cuda_stream);
+int32_t alz_apply_envelope_f32_host(const alz_plan* plan, const float* x_host, float* env_host, int64_t n_streams,
+                                    int64_t n_samples, int64_t x_stride, int64_t env_stride, int32_t decim, int32_t mode,
+                                    double g, double R);
+
+/*
  * Pinned host buffers for alz_apply_f32_host, placed on the NUMA node of CUDA device `device`
  * (< 0: the current device) so that several GPUs can run their PCIe copies at full rate at the same
  * time.  *numa_node (may be NULL) receives the node the pages were bound to, or -1 when the

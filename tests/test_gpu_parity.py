@@ -465,3 +465,28 @@ def test_wav_to_bank_to_chunks(gpu, designs, tmp_path, bits):
   row = y[1, 2, :lengths[1]]
   blocks = list(ab.chunks(row.tolist(), size=1024))
   assert b"".join(blocks) == np.concatenate([row, np.zeros(-len(row) % 1024, dtype=np.float32)]).astype("<f4").tobytes()
+
+
+@pytest.mark.parametrize("name,mode", [("slaney", "abs"), ("klapuri", "rms"), ("sampled", "squared")])
+def test_fused_envelope_consumer(gpu, name, mode):
+  """alz_apply_envelope_f32[_host]: |y| / y^2 -> one-pole lowpass -> every 48th value, inside the bank kernel, against the
+  unfused pipeline (bank output in float32, then the same lowpass in float64 on the host)."""
+  import audiolazy_b200 as ab
+  bank = ab.gammatone_bank(strategy=name)
+  S, T, D = 37, 48 * 100, 48
+  x = np.random.default_rng(3).uniform(-1, 1, (S, T)).astype(np.float32)
+  xd = gpu.torch.from_numpy(x).to(gpu.dev)
+  y = bank.apply(xd).cpu().numpy().astype(np.float64)
+  g, R = bank._envelope_pole(np.pi / 512)
+  r = np.abs(y) if mode == "abs" else y * y
+  e = np.zeros_like(r)
+  acc = np.zeros(r.shape[:2])
+  for n in range(T):
+    acc = g * r[:, :, n] + R * acc
+    e[:, :, n] = acc
+  want = (np.sqrt(e) if mode == "rms" else e)[:, :, D - 1::D]
+  got = bank.envelope(xd, decim=D, mode=mode).cpu().numpy()
+  assert got.shape == (S, 64, T // D)
+  assert rel_err(got, want) <= TOL
+  got_host = bank.envelope_host(x, decim=D, mode=mode)
+  assert np.array_equal(got_host, got)
