@@ -44,7 +44,7 @@
 extern "C" {
 #endif
 
-#define ALZ_ABI_VERSION 1
+#define ALZ_ABI_VERSION 2
 
 typedef enum alz_status {
   ALZ_OK = 0,

@@ -35,7 +35,7 @@ def test_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _build.LIB_PATH], capture_output=True, text=True).stdout
     exported = sorted(line.split()[-1] for line in out.splitlines() if " T alz_" in line)
     assert exported == declared
-  assert _capi.lib().alz_abi_version() == 1
+  assert _capi.lib().alz_abi_version() == 2
 
 
 def test_sass_is_sm100a_with_fp64_and_uniform_operands():
