@@ -481,10 +481,9 @@ def run_ours(args):
   if not args.no_e2e:
     e2e = run_e2e(args, torch, dev, plan, x, world, barrier, max_over_ranks)
 
-  # ---- multi-GPU secondary records: the batch scattered from rank 0; the channel-sharded north-star shape ----
-  multi = {}
-  if distributed and not args.no_extras:
-    del x, y
+  def multi_gpu_records():
+    """The batch scattered from rank 0; the channel-sharded north-star shape (all ranks take part)."""
+    multi = {}
     torch.cuda.empty_cache()
     if not distribute:
       try:
@@ -518,7 +517,9 @@ def run_ours(args):
                                                         4096, 4096, 10)
     except Exception as exc:
       multi["channel_sharded"] = {"error": repr(exc)}
+    return multi
 
+  line = None
   if rank == 0:
     peak, peak_src = peaks()
     achieved = BYTES_PER_IN_SAMPLE * S * Tn / (ms_per_step * 1e-3) / 1e9          # per GPU, GB/s
@@ -551,7 +552,6 @@ def run_ours(args):
       line["e2e"] = e2e
     if cfg5 is not None:
       line["cfg5"] = cfg5
-    line.update(multi)
     if world == 1 and not args.no_extras:
       line.update(extras(torch, dev, args, peak))
     if world == 1 and not args.no_cpu:
@@ -561,6 +561,23 @@ def run_ours(args):
       line["cpu_baseline"] = {"value": m["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": port.sample,
                               "min": m["min"], "max": m["max"], "reps": m["reps"], "host": cpu_info,
                               "python_exec_1core": python_exec_throughput(bank)}
+  if distributed and not args.no_extras:
+    # The secondary multi-GPU records run AFTER the headline has been measured; a watchdog thread makes sure a hung
+    # collective there cannot cost the line: after 300 s rank 0 prints what it has and every rank leaves.
+    def bail():
+      if rank == 0:
+        line["multi_gpu_records"] = "timed out"
+        print(json.dumps(line), flush=True)
+      os._exit(0)
+    dog = threading.Timer(300.0, bail)
+    dog.daemon = True
+    dog.start()
+    del x, y
+    multi = multi_gpu_records()
+    dog.cancel()
+    if rank == 0:
+      line.update(multi)
+  if rank == 0:
     print(json.dumps(line), flush=True)
   if distributed:
     dist.barrier()
