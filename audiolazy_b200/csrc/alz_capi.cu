@@ -991,7 +991,7 @@ static int envelope_check(const alz_plan* p, int64_t S, int64_t T, int64_t xs, i
   if (S < 0 || T < 0 || decim < 1 || mode < 0 || mode > 2) return fail(ALZ_ERR_INVALID, "bad argument");
   if (T % decim) return fail(ALZ_ERR_INVALID, "n_samples must be a multiple of the decimation factor");
   if (xs < T || es < T / decim) return fail(ALZ_ERR_INVALID, "row stride shorter than the row");
-  if (p->kind != ALZ_KIND_BIQUAD || p->K != 4 || p->monic != 2 || S > 65535ll * 32)
+  if (p->kind != ALZ_KIND_BIQUAD || p->K != 4 || p->monic == 0 || p->C * ALZ_COEF_STRIDE(4, p->NB0) <= 512 || S > 65535ll * 32)
     return fail(ALZ_ERR_UNSUPPORTED, "the envelope consumer is built for the gammatone banks (4 sections per channel)");
   return ALZ_OK;
 }

@@ -618,7 +618,7 @@ def run_e2e(args, torch, dev, plan, x, world, barrier, max_over_ranks):
          "note": "alz_apply_f32_host with pinned host buffers; PCIe-bound on the 256 B/sample output"}
   # second figure: the on-device envelope consumer shrinks the D2H stream by the decimation factor
   try:
-    decim = 48
+    decim = 64
     eh = _capi.HostBuffer((Se, C, Tn // decim))
     env_kw = dict(decim=decim, mode="abs", g=1.0 - 0.99388, R=0.99388)      # envelope.abs with the reference's default cutoff pi / 512
     plan.apply_envelope_host(xh.array, eh.array, **env_kw)
