@@ -601,6 +601,8 @@ void alz_plan_destroy(alz_plan* p) {
       if (p->pipe.done[i]) cudaEventDestroy(p->pipe.done[i]);
       cudaFree(p->pipe.dx[i]);
       cudaFree(p->pipe.dy[i]);
+      cudaFree(p->pipe.dst[i]);
+      cudaFree(p->pipe.des[i]);
     }
   }
   for (auto& ch : p->chunks) free(ch.block);
@@ -991,7 +993,7 @@ static int envelope_check(const alz_plan* p, int64_t S, int64_t T, int64_t xs, i
   if (S < 0 || T < 0 || decim < 1 || mode < 0 || mode > 2) return fail(ALZ_ERR_INVALID, "bad argument");
   if (T % decim) return fail(ALZ_ERR_INVALID, "n_samples must be a multiple of the decimation factor");
   if (xs < T || es < T / decim) return fail(ALZ_ERR_INVALID, "row stride shorter than the row");
-  if (p->kind != ALZ_KIND_BIQUAD || p->K != 4 || p->monic == 0 || p->C * ALZ_COEF_STRIDE(4, p->NB0) <= 512 || S > 65535ll * 32)
+  if (p->kind != ALZ_KIND_BIQUAD || p->K != 4 || p->C * ALZ_COEF_STRIDE(4, p->NB0) <= 512 || S > 65535ll * 32)
     return fail(ALZ_ERR_UNSUPPORTED, "the envelope consumer is built for the gammatone banks (4 sections per channel)");
   return ALZ_OK;
 }
@@ -1024,37 +1026,50 @@ int32_t alz_apply_envelope_f32_host(const alz_plan* cp, const float* xh, float* 
   // chunks of whole streams: <= 64 MiB of input per chunk (the output is decim times smaller than the bank's)
   long long Sc = std::max<long long>(32, (64LL << 20) / (Tp * 4) / 32 * 32);
   if (Sc > S) Sc = S;
+  AlzHostPipe& hp = p->pipe;
   const int NB = AlzHostPipe::NBUF;
-  cudaStream_t stream[NB];
-  float *dx[NB] = {}, *de[NB] = {};
-  double *dst[NB] = {}, *des[NB] = {};
-  int rc = ALZ_OK;
-  for (int i = 0; i < NB; ++i) {
-    ALZ_CUDA(cudaStreamCreateWithFlags(&stream[i], cudaStreamNonBlocking));
-    ALZ_CUDA(cudaMalloc(&dx[i], (size_t)Sc * Tp * 4));
-    ALZ_CUDA(cudaMalloc(&de[i], (size_t)Sc * C * Tdp * 4));
-    ALZ_CUDA(cudaMalloc(&dst[i], (size_t)p->state_doubles * Sc * C * 8));
-    ALZ_CUDA(cudaMalloc(&des[i], (size_t)Sc * C * 8));
+  if (!hp.ready) {
+    for (int i = 0; i < NB; ++i) {
+      ALZ_CUDA(cudaStreamCreateWithFlags(&hp.stream[i], cudaStreamNonBlocking));
+      ALZ_CUDA(cudaEventCreateWithFlags(&hp.done[i], cudaEventDisableTiming));
+    }
+    hp.ready = true;
   }
+  // staging buffers are kept in the plan between calls (grown on demand), as in alz_apply_f32_host
+  auto grow = [&](auto** bufs, size_t& have, size_t need) -> int {
+    if (have >= need) return ALZ_OK;
+    for (int i = 0; i < NB; ++i) {
+      ALZ_CUDA(cudaStreamSynchronize(hp.stream[i]));
+      cudaFree(bufs[i]);
+      bufs[i] = nullptr;
+    }
+    have = 0;
+    for (int i = 0; i < NB; ++i) ALZ_CUDA(cudaMalloc((void**)&bufs[i], need));
+    have = need;
+    return ALZ_OK;
+  };
+  int rc = grow(hp.dx, hp.dx_bytes, (size_t)Sc * Tp * 4);
+  if (rc == ALZ_OK) rc = grow(hp.dy, hp.dy_bytes, (size_t)Sc * C * Tdp * 4);
+  if (rc == ALZ_OK) rc = grow(hp.dst, hp.dst_bytes, (size_t)p->state_doubles * Sc * C * 8);
+  if (rc == ALZ_OK) rc = grow(hp.des, hp.des_bytes, (size_t)Sc * C * 8);
+  if (rc != ALZ_OK) return rc;
   int i = 0;
   for (long long s0 = 0; s0 < S && rc == ALZ_OK; s0 += Sc, ++i) {
     const long long n = std::min<long long>(Sc, S - s0);
     const int b = i % NB;
-    cudaStream_t st = stream[b];
-    cudaMemsetAsync(dst[b], 0, (size_t)p->state_doubles * n * C * 8, st);
-    cudaMemsetAsync(des[b], 0, (size_t)n * C * 8, st);
-    cudaError_t e = cudaMemcpy2DAsync(dx[b], Tp * 4, xh + s0 * xs, xs * 4, T * 4, n, cudaMemcpyHostToDevice, st);
+    cudaStream_t st = hp.stream[b];
+    cudaMemsetAsync(hp.dst[b], 0, (size_t)p->state_doubles * n * C * 8, st);
+    cudaMemsetAsync(hp.des[b], 0, (size_t)n * C * 8, st);
+    cudaError_t e = cudaMemcpy2DAsync(hp.dx[b], Tp * 4, xh + s0 * xs, xs * 4, T * 4, n, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e)); break; }
-    rc = envelope_impl(p, dx[b], de[b], dst[b], des[b], n * C, n, T, Tp, Tdp, decim, mode, g, R, st);
+    rc = envelope_impl(p, hp.dx[b], hp.dy[b], hp.dst[b], hp.des[b], n * C, n, T, Tp, Tdp, decim, mode, g, R, st);
     if (rc != ALZ_OK) break;
-    e = cudaMemcpy2DAsync(eh + s0 * C * es, es * 4, de[b], Tdp * 4, Td * 4, n * C, cudaMemcpyDeviceToHost, st);
+    e = cudaMemcpy2DAsync(eh + s0 * C * es, es * 4, hp.dy[b], Tdp * 4, Td * 4, n * C, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess) { rc = fail(ALZ_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e)); break; }
   }
   for (int k = 0; k < NB; ++k) {
-    cudaError_t e = cudaStreamSynchronize(stream[k]);
+    cudaError_t e = cudaStreamSynchronize(hp.stream[k]);
     if (e != cudaSuccess && rc == ALZ_OK) rc = fail(ALZ_ERR_CUDA, "pipeline failed: %s", cudaGetErrorString(e));
-    cudaFree(dx[k]); cudaFree(de[k]); cudaFree(dst[k]); cudaFree(des[k]);
-    cudaStreamDestroy(stream[k]);
   }
   return rc;
 }

@@ -55,7 +55,7 @@ alz_biquad_envelope_kernel(const __grid_constant__ AlzTileArgs a, const __grid_c
 
 template <int K, int NB, int NB0, int ZMASK>
 static int launch_envelope_t(const alz_plan* p, AlzTileArgs ta, cudaStream_t st) {
-  if (p->monic == 0 || p->coef_small || p->chunks.size() != 1)
+  if (p->coef_small || p->chunks.size() != 1)
     return alzi_fail(ALZI_ERR_UNSUPPORTED, "envelope consumer: gammatone-bank plans only");
   CUtensorMap tmx, tmy;
   if (!alzi_make_tensor_maps(ta, &tmx, &tmy)) return alzi_fail(ALZI_ERR_UNSUPPORTED, "envelope consumer needs 16-byte aligned x rows");
@@ -64,7 +64,8 @@ static int launch_envelope_t(const alz_plan* p, AlzTileArgs ta, cudaStream_t st)
   ta.groups = (int)groups;
   void* args[4] = {(void*)&ta, p->chunks[0].block, (void*)&tmx, (void*)&tmy};
   const void* kern = p->monic == 2 ? (const void*)alz_biquad_envelope_kernel<K, NB, 2, kCoefLarge, NB0, ZMASK>
-                                   : (const void*)alz_biquad_envelope_kernel<K, NB, 1, kCoefLarge, NB0, ZMASK>;
+                   : p->monic == 1 ? (const void*)alz_biquad_envelope_kernel<K, NB, 1, kCoefLarge, NB0, ZMASK>
+                                   : (const void*)alz_biquad_envelope_kernel<K, NB, 0, kCoefLarge, NB0, ZMASK>;
   ALZ_CUDA(cudaLaunchKernel(kern, dim3((unsigned)p->chunks[0].npos, (unsigned)groups), dim3(32), args, ALZ_TMA_SMEM_FOR(ta.paired), st));
   ALZ_CUDA(cudaGetLastError());
   alzi_launches.fetch_add(1, std::memory_order_relaxed);

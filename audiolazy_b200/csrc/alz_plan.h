@@ -39,7 +39,9 @@ struct AlzHostPipe {   // lazily created resources of alz_apply_f32_host
   cudaEvent_t done[NBUF] = {};
   float* dx[NBUF] = {};
   float* dy[NBUF] = {};
-  size_t dx_bytes = 0, dy_bytes = 0;
+  double* dst[NBUF] = {};     // envelope entry: per-chunk recurrence states and lowpass states
+  double* des[NBUF] = {};
+  size_t dx_bytes = 0, dy_bytes = 0, dst_bytes = 0, des_bytes = 0;
   bool ready = false;
 };
 
