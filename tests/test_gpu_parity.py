@@ -490,3 +490,29 @@ def test_fused_envelope_consumer(gpu, name, mode):
   assert rel_err(got, want) <= TOL
   got_host = bank.envelope_host(x, decim=D, mode=mode)
   assert np.array_equal(got_host, got)
+
+
+def test_cfg3_at_full_length_and_cfg5_shape(gpu, designs):
+  """BASELINE config 3 at its full 10^6 samples (one stream through the 64-channel bank; the time-parallel path) against
+  the oracle over the WHOLE length, and config 5's per-GPU shape (8192 streams x 8192 samples) against the oracle on a
+  few rows plus the duplicated-half identity."""
+  torch = gpu.torch
+  bank = designs["bank_slaney"]
+  plan = gpu.capi.Plan(bank)
+  x = signal(33, 1000000)[None, :]
+  y = gpu.run(plan, x)
+  want = oracle.bank_apply(x, bank)
+  assert rel_err(y, want) <= TOL
+  del y, want
+  S, T, C = 8192, 8192, 64
+  g = torch.Generator(device=gpu.dev)
+  g.manual_seed(5)
+  xd = torch.rand((S, T), device=gpu.dev, generator=g) * 2 - 1
+  xd[S // 2:] = xd[:S // 2]
+  yd = torch.empty((S, C, T), dtype=torch.float32, device=gpu.dev)
+  st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=gpu.dev)
+  plan.apply(xd.data_ptr(), yd.data_ptr(), st.data_ptr(), S, T, T, T, torch.cuda.current_stream().cuda_stream)
+  torch.cuda.synchronize()
+  assert torch.equal(yd[:S // 2], yd[S // 2:])
+  rows = [0, 31, 32, 4095, 2049, 777]
+  assert rel_err(yd[rows].cpu().numpy(), oracle.bank_apply(xd[rows].cpu().numpy(), bank)) <= TOL
