@@ -965,7 +965,9 @@ int32_t alz_apply_f32_ex(const alz_plan* p, const float* x, float* y, double* st
   if (S == 0 || T == 0) return ALZ_OK;
   if (!x || !y || !state) return fail(ALZ_ERR_INVALID, "null buffer");
   if (xs < T || ys < T) return fail(ALZ_ERR_INVALID, "row stride shorter than n_samples");
-  if (y_stream_stride < (int64_t)p->C * ys) return fail(ALZ_ERR_INVALID, "stream stride shorter than n_channels rows");
+  // rows must not overlap: stream-major (stream stride >= C rows) or channel-major (row stride >= S stream strides)
+  if (y_stream_stride < T || !(y_stream_stride >= (int64_t)p->C * ys || ys >= S * y_stream_stride))
+    return fail(ALZ_ERR_INVALID, "output rows overlap: need y_stream_stride >= n_channels * y_stride or y_stride >= n_streams * y_stream_stride");
   int cur = -1;
   ALZ_CUDA(cudaGetDevice(&cur));
   if (cur != p->device) ALZ_CUDA(cudaSetDevice(p->device));

@@ -187,7 +187,9 @@ int32_t alz_apply_f32(const alz_plan* plan, const float* x_dev, float* y_dev,
  * consecutive STREAMS: row (s, c) starts at y_dev + s * y_stream_stride + c * y_stride.  Lets a
  * plan that holds a SLICE of a bank's channels (channel-sharded multi-GPU, audiolazy_b200/parallel.py)
  * write its rows straight into the full y[S][C_total][T] tensor -- local, or a peer GPU's over
- * NVLink -- with y_dev offset to its first channel.  y_stream_stride >= n_channels * y_stride.
+ * NVLink -- with y_dev offset to its first channel; y_stream_stride >= n_channels * y_stride.  It also
+ * expresses the CHANNEL-MAJOR layout y[C][S][T]: y_stream_stride = T, y_stride = n_streams * T (then
+ * y_stride >= n_streams * y_stream_stride): the 32 rows a warp stores are 64 KB apart instead of C * 64 KB.
  * The time-parallel evaluation of few long streams is not used on this entry.
  */
 int32_t alz_apply_f32_ex(const alz_plan* plan, const float* x_dev, float* y_dev, double* state_dev,

@@ -19,7 +19,13 @@ st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=dev)
 cur = torch.cuda.current_stream().cuda_stream
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
 ts = []
+major = os.environ.get("ALZ_PROF_LAYOUT", "stream")       # "channel": y[C][S][T] through alz_apply_f32_ex
 for i in range(iters):
-  e0.record(); plan.apply(xd.data_ptr(), yd.data_ptr(), st.data_ptr(), S, T, T, T, cur); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+  e0.record()
+  if major == "channel":
+    plan.apply_ex(xd.data_ptr(), yd.data_ptr(), st.data_ptr(), S, T, T, S * T, T, cur)
+  else:
+    plan.apply(xd.data_ptr(), yd.data_ptr(), st.data_ptr(), S, T, T, T, cur)
+  e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 ms = min(ts)
-print("%s C=%d S=%d T=%d best %.3f ms  %.3f G in-samples/s  %.1f GB/s" % (name, C, S, T, ms, S * T / ms / 1e6, S * T * (4 + 4 * C) / ms / 1e6), ["%.3f" % t for t in ts])
+print("[%s-major] " % major + "%s C=%d S=%d T=%d best %.3f ms  %.3f G in-samples/s  %.1f GB/s" % (name, C, S, T, ms, S * T / ms / 1e6, S * T * (4 + 4 * C) / ms / 1e6), ["%.3f" % t for t in ts])
