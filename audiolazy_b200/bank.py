@@ -33,8 +33,8 @@ class FilterBank(list):
 
   * ``bank(seq)`` -> list of Streams, one per channel (``[f(seq_copy) for f in bank]``).
   * ``bank.apply(x)`` -> CUDA tensor ``y[S, C, T]`` for a CUDA float32 tensor ``x[S, T]``
-    of ``S`` independent streams; pass ``state=bank.new_state(S)`` to continue streams
-    across calls.
+    of ``S`` independent streams (``channel_major=True``: ``y[C, S, T]``); pass
+    ``state=bank.new_state(S)`` to continue streams across calls.
   * ``bank.apply_host(x)`` -> the same through numpy host buffers (copies inside).
   """
 
@@ -79,14 +79,14 @@ class FilterBank(list):
     return _engine.bank_streams(secs, seq, [s[0] for s in seeds], [s[1] for s in seeds])
 
   # -- batch API -----------------------------------------------------------------------
-  def apply(self, x, state=None, out=None):
+  def apply(self, x, state=None, out=None, channel_major=False):
     db = self.device_bank()
     if x.dim() == 1:
       x = x.unsqueeze(0)
     if state is None:
       state = self.new_state(x.shape[0])
     self._check_state(state, x.shape[0], db)
-    return db.apply(x, state.tensor, out=out)
+    return db.apply(x, state.tensor, out=out, channel_major=channel_major)
 
   def _check_state(self, state, n_streams, db):
     if state.n_streams != n_streams:

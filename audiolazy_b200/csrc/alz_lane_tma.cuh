@@ -205,21 +205,7 @@ __device__ __forceinline__ void alz_run_warp_tma(const AlzTileArgs& a, const Cor
     alz_fence_async_smem();                          // my generic-proxy writes -> visible to the TMA store
     __syncwarp();
     const bool last = i + 1 == ntiles;
-    if ((a.exp & 4) && !Post::active && a.vP == 0) {
-      // ALZ_EXP & 4 (experiment): the tile leaves through st.global.v4 (4 rows x 128 B per instruction) instead of the TMA
-      const int sub = lane >> 3, cc = lane & 7;
-      const float* tile = reinterpret_cast<const float*>(smem) + j * (ALZ_TMA_TILE_BYTES / 4);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = it * 4 + sub;
-        if (s0 + row < a.S && t0 + cc * 4 < tlen) {
-          const float4 v = *reinterpret_cast<const float4*>(tile + row * 32 + ((cc ^ (row & 7)) << 2));
-          alz_st_v4(a.y + (s0 + row) * a.ysS + (long long)c * a.ys + tbeg + t0 + cc * 4, v);
-        }
-      }
-      __syncwarp();
-    }
-    if (lane == 0 && !(a.exp & 6) && !Post::active) {
+    if (lane == 0 && !(a.exp & 2) && !Post::active) {
       if (NG == 1) {
         if (!(tail_by_lanes && last)) alz_tma_store_4d(tmy, tb + t0, st1, st2, st3, tile0 + j * ALZ_TMA_TILE_BYTES);   // ragged last tile: stored after the loop
         alz_bulk_commit();

@@ -314,6 +314,29 @@ def extras(torch, dev, args, peak):
   except Exception as exc:                                            # a secondary record must never kill the headline
     out["strategies"] = {"error": repr(exc)}
   try:
+    # the same bank writing y[C][S][T] (alz_apply_f32_ex): a warp's 32 output rows are 64 KB apart instead of 4 MB
+    plan = bank_sections(args.strategy).device_bank().plan
+    xx = torch.rand((S, Tn), device=dev) * 2 - 1
+    yy = torch.empty((C, S, Tn), dtype=torch.float32, device=dev)
+    st = torch.zeros(plan.state_doubles(S), dtype=torch.float64, device=dev)
+    cur = torch.cuda.current_stream(dev).cuda_stream
+    times = []
+    for i in range(7):
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      plan.apply_ex(xx.data_ptr(), yy.data_ptr(), st.data_ptr(), S, Tn, Tn, S * Tn, Tn, cur)
+      e1.record()
+      torch.cuda.synchronize(dev)
+      if i >= 2:
+        times.append(e0.elapsed_time(e1))
+    ms = statistics.median(times)
+    gbs = BYTES_PER_IN_SAMPLE * S * Tn / (ms * 1e-3) / 1e9
+    out["channel_major_layout"] = {"ms": ms, "input_samples_per_s": S * Tn / (ms * 1e-3), "gbs": gbs, "roofline_frac": gbs / peak,
+                                   "note": "secondary: output written as y[C][S][T] instead of the headline's y[S][C][T]"}
+    del xx, yy, st
+  except Exception as exc:
+    out["channel_major_layout"] = {"error": repr(exc)}
+  try:
     import scipy.signal as sig
     sos = sig.butter(8, 0.25, output="sos")
     cfg2 = _capi.Plan([[(r[:3].tolist(), r[3:].tolist()) for r in sos]])

@@ -167,6 +167,18 @@ def test_nccl_sharding_parity_under_torchrun(ab):
   assert out.returncode == 0 and "PARITY OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
+def test_channel_major_output(ab):
+  """``bank.apply(x, channel_major=True)`` writes y[C][S][T] (alz_apply_f32_ex with swapped strides): same values."""
+  import torch
+  bank = ab.gammatone_bank(freqs=ab.erb_space(n=12), strategy="klapuri")
+  x = torch.from_numpy(np.stack([signal(80 + i, 4099) for i in range(70)])).cuda()
+  y = bank.apply(x)
+  ycm = bank.apply(x, channel_major=True)
+  assert ycm.shape == (12, 70, 4099) and torch.equal(ycm.permute(1, 0, 2), y)
+  x4 = x[:, :4096].contiguous()                      # 16-byte aligned rows: the TMA engine
+  assert torch.equal(bank.apply(x4, channel_major=True).permute(1, 0, 2), bank.apply(x4))
+
+
 def test_sharded_bank_single_process(ab):
   """world size 1 (no process group): the sharded wrapper degenerates to the bank itself; state=None is a fresh
   state on every call, as FilterBank.apply."""
