@@ -32,7 +32,7 @@ PLAN_PARALLEL = 16
 SYMBOLS = (
   "alz_last_error", "alz_abi_version", "alz_device_count", "alz_set_device", "alz_plan_create", "alz_plan_create_ex",
   "alz_plan_destroy", "alz_plan_taps", "alz_apply_tv_f32", "alz_plan_tiers", "alz_apply_f32_ex", "alz_host_alloc",
-  "alz_host_free", "alz_apply_sum_f32", "alz_apply_envelope_f32", "alz_apply_envelope_f32_host",
+  "alz_host_free", "alz_stream_create_partition", "alz_stream_destroy_partition", "alz_apply_sum_f32", "alz_apply_envelope_f32", "alz_apply_envelope_f32_host",
   "alz_plan_info_get", "alz_plan_state_doubles", "alz_state_init", "alz_plan_history", "alz_apply_f32",
   "alz_apply_f32_host", "alz_sum_channels_f32", "alz_freq_response_f64", "alz_launch_count",
 )
@@ -103,6 +103,10 @@ def lib():
   L.alz_apply_envelope_f32.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, f64, f64, vp]
   L.alz_apply_envelope_f32_host.restype = i32
   L.alz_apply_envelope_f32_host.argtypes = [vp, vp, vp, i64, i64, i64, i64, i32, i32, f64, f64]
+  L.alz_stream_create_partition.restype = i32
+  L.alz_stream_create_partition.argtypes = [i32, i32, ctypes.POINTER(vp), ctypes.POINTER(i32)]
+  L.alz_stream_destroy_partition.restype = i32
+  L.alz_stream_destroy_partition.argtypes = [vp]
   L.alz_host_alloc.restype = i32
   L.alz_host_alloc.argtypes = [ctypes.POINTER(vp), i64, i32, ctypes.POINTER(i32)]
   L.alz_host_free.restype = i32
@@ -271,6 +275,22 @@ class Plan(object):
     x_stride = x.strides[0] // 4 if S > 1 else max(T, 1)   # a length-1 axis may carry any stride
     _check(lib().alz_apply_f32_host(self._h, x.ctypes.data, y.ctypes.data, state_ptr, S, T, x_stride, T))
     return y
+
+
+class PartitionStream(object):
+  """A CUDA stream confined to ``sm_count`` SMs of ``device`` (green context, ``alz_stream_create_partition``).
+  ``.handle`` is the ``cudaStream_t``; ``.sm_count`` what was granted. Wrap it with ``torch.cuda.ExternalStream``."""
+
+  def __init__(self, sm_count, device=-1):
+    h, granted = ctypes.c_void_p(), ctypes.c_int32(0)
+    _check(lib().alz_stream_create_partition(int(device), int(sm_count), ctypes.byref(h), ctypes.byref(granted)))
+    self.handle = h.value
+    self.sm_count = granted.value
+
+  def close(self):
+    h, self.handle = self.handle, None
+    if h:
+      _check(lib().alz_stream_destroy_partition(h))
 
 
 class HostBuffer(object):

@@ -102,6 +102,19 @@ static alz_encode_tiled_fn get_encode_tiled() {
   return fn;
 }
 
+template <class F>
+static bool driver_fn(const char* name, F* out) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+    cudaGetLastError();
+    return false;
+  }
+  *out = (F)p;
+  return true;
+}
+static std::map<void*, CUgreenCtx> g_partitions;
+
 // x[S][T] (row stride xs) and y[S][C][T] (row stride ys) as tiled tensor maps with 32-sample boxes.
 bool alzi_make_tensor_maps(const AlzTileArgs& ta, CUtensorMap* tmx, CUtensorMap* tmy) {
   alz_encode_tiled_fn enc = get_encode_tiled();
@@ -1383,6 +1396,72 @@ int32_t alz_host_free(void* ptr) {
   cudaHostUnregister(ptr);
   cudaGetLastError();
   munmap(ptr, len);
+  return ALZ_OK;
+}
+
+// ---- a stream confined to a partition of the SMs (green context) ----------------------------------------
+// Channel-sharded multi-GPU: every rank's bank kernel is short and its one-warp CTAs sit on ALL SMs for the whole
+// kernel; an NCCL kernel (hundreds of threads x ~100 registers per CTA) needs an SM that is nearly EMPTY, so a broadcast
+// issued on a side stream waits for the bank kernel to end (measured: step = kernel + broadcast).  A stream of a green
+// context that owns only `sm_count` SMs keeps the bank kernel off the others, which NCCL's CTAs then find free.
+int32_t alz_stream_create_partition(int32_t device, int32_t sm_count, void** stream_out, int32_t* sm_granted) {
+  if (!stream_out || sm_count < 8) return fail(ALZ_ERR_INVALID, "bad argument");
+  *stream_out = nullptr;
+  int dev = device;
+  if (dev < 0) ALZ_CUDA(cudaGetDevice(&dev));
+  ALZ_CUDA(cudaSetDevice(dev));
+  ALZ_CUDA(cudaFree(nullptr));                           // the primary context exists
+  CUresult (*devGet)(CUdevice*, int) = nullptr;
+  CUresult (*getRes)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int) = nullptr;
+  CUresult (*genDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*ctxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*ctxDestroy)(CUgreenCtx) = nullptr;
+  CUresult (*streamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+  if (!driver_fn("cuDeviceGet", &devGet) || !driver_fn("cuDeviceGetDevResource", &getRes) ||
+      !driver_fn("cuDevSmResourceSplitByCount", &split) || !driver_fn("cuDevResourceGenerateDesc", &genDesc) ||
+      !driver_fn("cuGreenCtxCreate", &ctxCreate) || !driver_fn("cuGreenCtxDestroy", &ctxDestroy) ||
+      !driver_fn("cuGreenCtxStreamCreate", &streamCreate))
+    return fail(ALZ_ERR_UNSUPPORTED, "this driver has no green contexts");
+  CUdevice cudev;
+  CUdevResource all, part, rest;
+  unsigned int groups = 1;
+  CUdevResourceDesc desc;
+  CUgreenCtx gctx;
+  CUstream stream;
+  CUresult r = devGet(&cudev, dev);
+  if (r == CUDA_SUCCESS) r = getRes(cudev, &all, CU_DEV_RESOURCE_TYPE_SM);
+  if (r == CUDA_SUCCESS) r = split(&part, &groups, &all, &rest, 0, (unsigned)sm_count);
+  if (r == CUDA_SUCCESS && groups < 1) r = CUDA_ERROR_INVALID_VALUE;
+  if (r == CUDA_SUCCESS) r = genDesc(&desc, &part, 1);
+  if (r == CUDA_SUCCESS) r = ctxCreate(&gctx, desc, cudev, CU_GREEN_CTX_DEFAULT_STREAM);
+  if (r != CUDA_SUCCESS) return fail(ALZ_ERR_CUDA, "green context with %d SMs failed (CUresult %d)", sm_count, (int)r);
+  r = streamCreate(&stream, gctx, CU_STREAM_NON_BLOCKING, 0);
+  if (r != CUDA_SUCCESS) { ctxDestroy(gctx); return fail(ALZ_ERR_CUDA, "green-context stream failed (CUresult %d)", (int)r); }
+  {
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    g_partitions[(void*)stream] = gctx;
+  }
+  if (sm_granted) *sm_granted = (int32_t)part.sm.smCount;
+  *stream_out = (void*)stream;
+  return ALZ_OK;
+}
+
+int32_t alz_stream_destroy_partition(void* stream) {
+  if (!stream) return ALZ_OK;
+  CUgreenCtx gctx;
+  {
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    auto it = g_partitions.find(stream);
+    if (it == g_partitions.end()) return fail(ALZ_ERR_INVALID, "not a partition stream");
+    gctx = it->second;
+    g_partitions.erase(it);
+  }
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaStreamDestroy((cudaStream_t)stream);
+  CUresult (*ctxDestroy)(CUgreenCtx) = nullptr;
+  if (driver_fn("cuGreenCtxDestroy", &ctxDestroy)) ctxDestroy(gctx);
+  cudaGetLastError();
   return ALZ_OK;
 }
 

@@ -203,8 +203,8 @@ class ShardedBank(object):
                      self.n_channels * T, torch.cuda.current_stream(x.device).cuda_stream)
     return peer_out
 
-  def pipeline(self, x_blocks, y, state):
-    return BroadcastPipeline(self, x_blocks, y, state)
+  def pipeline(self, x_blocks, y, state, compute_sms=None):
+    return BroadcastPipeline(self, x_blocks, y, state, compute_sms=compute_sms)
 
 
 class BroadcastPipeline(object):
@@ -215,12 +215,26 @@ class BroadcastPipeline(object):
   ``step()`` issues, without any host synchronisation: (side stream) NCCL broadcast of the NEXT block once the
   kernel that last read that buffer is done; (main stream) wait for THIS block's broadcast, kernel."""
 
-  def __init__(self, sharded, x_blocks, y, state, src=0):
+  def __init__(self, sharded, x_blocks, y, state, src=0, compute_sms=None):
     import torch
     self.sb, self.x, self.y, self.state, self.src = sharded, x_blocks, y, state, src
     self.torch = torch
     dev = y.device
     self.side = torch.cuda.Stream(device=dev, priority=-1)
+    # ``compute_sms``: run the bank kernels on a green-context stream that owns only that many SMs. The kernel's
+    # one-warp CTAs otherwise sit on EVERY SM for the whole kernel and an NCCL CTA (hundreds of threads x ~100
+    # registers) needs a nearly empty SM: the side-stream broadcast then waits for the kernel to end (measured).
+    self.partition = None
+    self.compute = None
+    if compute_sms == "auto":
+      # a partition is free of charge when the kernel under-fills the machine anyway (one-warp CTAs: 24 fit on an SM)
+      n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+      ctas = len(sharded.local) * ((x_blocks[0].shape[0] + 31) // 32)
+      compute_sms = (n_sm - 20) // 8 * 8 if (sharded.world > 1 and ctas <= 12 * n_sm) else None
+    if compute_sms:
+      from . import _capi
+      self.partition = _capi.PartitionStream(compute_sms, dev.index)
+      self.compute = torch.cuda.ExternalStream(self.partition.handle, device=dev)
     self.bc_done = [torch.cuda.Event(), torch.cuda.Event()]
     self.i = 0
     self.primed = False
@@ -244,13 +258,35 @@ class BroadcastPipeline(object):
       self._broadcast(j)
       self.primed = True
     self._broadcast(j ^ 1)
-    main.wait_event(self.bc_done[j])
-    self.sb.local.apply(self.x[j], state=self.state, out=self.y)
+    if self.compute is None:
+      main.wait_event(self.bc_done[j])
+      self.sb.local.apply(self.x[j], state=self.state, out=self.y)
+    else:
+      self.compute.wait_stream(main)
+      self.compute.wait_event(self.bc_done[j])
+      with torch.cuda.stream(self.compute):
+        self.sb.local.apply(self.x[j], state=self.state, out=self.y)
+      main.wait_stream(self.compute)
     self.i += 1
 
-  def compute_only(self):
-    """The same kernel on an already resident block (the no-collective reference time)."""
-    self.sb.local.apply(self.x[0], state=self.state, out=self.y)
+  def compute_only(self, partition=False):
+    """The same kernel on an already resident block (the no-collective reference time; ``partition=True``: on the
+    SM partition, when there is one)."""
+    if partition and self.compute is not None:
+      torch = self.torch
+      main = torch.cuda.current_stream(self.y.device)
+      self.compute.wait_stream(main)
+      with torch.cuda.stream(self.compute):
+        self.sb.local.apply(self.x[0], state=self.state, out=self.y)
+      main.wait_stream(self.compute)
+    else:
+      self.sb.local.apply(self.x[0], state=self.state, out=self.y)
+
+  def close(self):
+    if self.partition is not None:
+      self.torch.cuda.synchronize(self.y.device)
+      self.partition.close()
+      self.partition = self.compute = None
 
   def drain(self):
     """Order the main stream after every outstanding broadcast (call before reusing the buffers by hand)."""

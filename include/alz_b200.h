@@ -261,6 +261,16 @@ int32_t alz_apply_sum_f32(const alz_plan* plan, const float* x_dev, float* out_d
                           void* cuda_stream);
 
 /*
+ * A CUDA stream whose kernels run on a partition of `sm_count` SMs only (green context; the granted count -- a
+ * multiple of 8 on this architecture -- is returned in *sm_granted).  For the channel-sharded multi-GPU pipeline: the
+ * bank kernel's one-warp CTAs otherwise occupy every SM for the whole kernel and an NCCL kernel issued on a side stream
+ * (its CTAs need a nearly empty SM) waits for it; launched on a partition stream the bank kernel leaves the other SMs to
+ * NCCL and the broadcast of the next input block really overlaps.  Pass the handle as `cuda_stream` to the apply entries.
+ */
+int32_t alz_stream_create_partition(int32_t device, int32_t sm_count, void** stream_out, int32_t* sm_granted);
+int32_t alz_stream_destroy_partition(void* stream);
+
+/*
  * ParallelFilter reduction: out[s][t] = ((y[s][0][t] + y[s][1][t]) + ...) over
  * the channel axis, left associated as reference lazy_filters.py:1053-1054.
  * Device buffers; asynchronous on `cuda_stream`.

@@ -64,6 +64,23 @@ for i, b in enumerate(blocks):
   torch.cuda.synchronize()
   check("pipeline block %d" % i, torch.equal(y, truth[i][:, sb.c_lo:sb.c_hi]))
 pipe.drain()
+# the same pipeline with the bank kernel on an SM partition (green context): identical values
+try:
+  st_p = sb.local.new_state(S)
+  pp = sb.pipeline(xb, y, st_p, compute_sms=128)
+  if rank == 0:
+    xb[0].copy_(blocks[0])
+  for i, b in enumerate(blocks):
+    if rank == 0 and i + 1 < len(blocks):
+      xb[(i + 1) & 1].copy_(blocks[i + 1])
+    pp.step()
+    torch.cuda.synchronize()
+    check("partitioned pipeline block %d" % i, torch.equal(y, truth[i][:, sb.c_lo:sb.c_hi]))
+  pp.drain()
+  pp.close()
+except Exception as exc:
+  if rank == 0:
+    print("SM partition unavailable: %r" % (exc,), file=sys.stderr)
 # ---- in-place gather ----------------------------------------------------------------------------
 gbuf = sb.alloc_gather(S, T)
 sb.gather_output_into(y, gbuf)
