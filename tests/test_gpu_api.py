@@ -179,6 +179,36 @@ def test_channel_major_output(ab):
   assert torch.equal(bank.apply(x4, channel_major=True).permute(1, 0, 2), bank.apply(x4))
 
 
+def test_partition_stream(ab):
+  """alz_stream_create_partition: a stream whose kernels run on a subset of the SMs (green context); the bank gives the
+  same bits there (what BroadcastPipeline(compute_sms=...) relies on to leave SMs to NCCL)."""
+  import torch
+  from audiolazy_b200 import _capi
+  try:
+    part = _capi.PartitionStream(128)
+  except _capi.NativeError as exc:
+    pytest.skip("no green contexts here: %s" % exc)
+  try:
+    assert 8 <= part.sm_count <= 148 and part.sm_count % 8 == 0
+    bank = ab.gammatone_bank(freqs=ab.erb_space(n=8), strategy="slaney")
+    x = torch.from_numpy(np.stack([signal(90 + i, 4096) for i in range(40)])).cuda()
+    want = bank.apply(x)
+    ext = torch.cuda.ExternalStream(part.handle, device=x.device)
+    ext.wait_stream(torch.cuda.current_stream())
+    state = bank.new_state(40)
+    out = torch.empty_like(want)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(ext):
+      bank.apply(x, state=state, out=out)
+    ext.synchronize()
+    assert torch.equal(out, want)
+  finally:
+    torch.cuda.synchronize()
+    part.close()
+  with pytest.raises(ValueError):
+    _capi.PartitionStream(4)                            # fewer than the architecture's minimum of 8 SMs
+
+
 def test_sharded_bank_single_process(ab):
   """world size 1 (no process group): the sharded wrapper degenerates to the bank itself; state=None is a fresh
   state on every call, as FilterBank.apply."""
